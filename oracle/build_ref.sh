@@ -1,0 +1,49 @@
+#!/usr/bin/env bash
+# build_ref.sh -- compile the reference's OWN implementation of the hot path as a host checker.
+#
+# TEST INFRASTRUCTURE ONLY.  Reads the sources where they lie under $OVRFSR_REFERENCE
+# (default /root/reference, read-only), writes ONLY oracle/_ref/libovrfsr_ref.so
+# (git-ignored, not gpurun-ignored so the prebuilt .so travels to the GPU box).
+# No reference source is copied into the repository: the extracted kernel lines live
+# in a temporary directory that is removed on exit.
+#
+# What is compiled (reference @ 2146b45):
+#   consts_ref.cpp : ffx_a.h + ffx_fsr1.h + NIS_Config.h under A_CPU, as shipped
+#   fsr_ref.cpp    : ffx_fsr1.h:239-437 (EASU), :684-769 (RCAS), ffx_a.h:1843-1845, behind an HLSL type shim
+#   nis_ref.cpp    : NIS_Scaler.h verbatim (twice: NIS_SCALER=1 and 0) behind an HLSL type shim
+# The reference's own build system (Visual Studio + fxc, src/CMakeLists.txt:155-170) is not run.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${OVRFSR_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+CXX="${CXX:-g++}"
+CXXFLAGS="-O2 -ffp-contract=off -fno-fast-math -fPIC -std=c++17 -pthread -w"
+
+if [ ! -f "$REF/src/fsr/ffx_fsr1.h" ]; then
+  echo "build_ref: $REF not present; keeping prebuilt $OUT (if any)"; exit 0
+fi
+
+TMP="$(mktemp -d)"; trap 'rm -rf "$TMP"' EXIT
+mkdir -p "$OUT"
+FSR1="$REF/src/fsr/ffx_fsr1.h"; FFXA="$REF/src/fsr/ffx_a.h"
+
+# anchors: fail loudly if the pinned line numbers drift
+sed -n '239p' "$FSR1" | grep -q 'void FsrEasuTapF('  || { echo "anchor 239 moved"; exit 1; }
+sed -n '437p' "$FSR1" | grep -q 'pix=min(max4'        || { echo "anchor 437 moved"; exit 1; }
+sed -n '684p' "$FSR1" | grep -q 'void FsrRcasF('      || { echo "anchor 684 moved"; exit 1; }
+sed -n '769p' "$FSR1" | grep -q 'return;}'            || { echo "anchor 769 moved"; exit 1; }
+sed -n '1843p' "$FFXA" | grep -q 'APrxLoRcpF1'        || { echo "anchor 1843 moved"; exit 1; }
+
+HLSL2CPP='s/\b(inout|out) (A[A-Z]+[0-9])\b/\2\&/g'
+sed -n '239,437p' "$FSR1" | sed -E "$HLSL2CPP" > "$TMP/easu_lines.inc"
+sed -n '684,769p' "$FSR1" | sed -E "$HLSL2CPP" > "$TMP/rcas_lines.inc"
+sed -n '1843,1845p' "$FFXA" > "$TMP/ffx_prx.inc"
+
+OBJS=()
+for f in consts_ref fsr_ref nis_ref; do
+  [ -f "$HERE/ref_shim/$f.cpp" ] || continue
+  $CXX $CXXFLAGS -I"$REF/src" -I"$TMP" -c "$HERE/ref_shim/$f.cpp" -o "$TMP/$f.o"
+  OBJS+=("$TMP/$f.o")
+done
+$CXX -shared -pthread -o "$OUT/libovrfsr_ref.so" "${OBJS[@]}"
+echo "build_ref: wrote $OUT/libovrfsr_ref.so"
