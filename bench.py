@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- stereo eye-pairs/s of the FSR1 EASU+RCAS pass (BASELINE.json metric) on N B200s.
+
+Workload (config.workload): BASELINE.json configs[1] = SURVEY.md C2: stereo 1683x1869 -> 2244x2492 RGBA8,
+renderScale 0.75, sharpness 0.9, FSR path, radius 2.0 (mask off: EVERY pixel takes EASU+RCAS; the reference's
+default radius 0.5 is reported beside it as `masked_r0.5`).  A "step" is one pass of the hot path over a batch
+of POOL distinct stereo pairs per GPU; the input pool (POOL x 25 MB) is larger than the 126 MB L2, so no step
+re-reads inputs from L2 (config.l2: "inputs larger than L2").
+
+  value     : whole-job pairs/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same metric through PostProcessor.apply_host with pinned HOST buffers (H2D + kernels + D2H timed)
+  roofline  : dominant kernel (EASU) algorithmic bytes / its mean launch time (CUDA events on the launch
+              stream, second instrumented pass) against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the reference's own lines (oracle/_ref, kind "reference") or the restated oracle ("port")
+              on the box's host cores, one stereo pair, rank 0 at N=1 only
+  --impl reference : the CPU reference arm (same metric/config), rank 0 only under torchrun
+
+Multi-GPU: frames are independent -> each rank processes its own pool, no data-path
+collective; NCCL only broadcasts the constant block from rank 0 and forms the barriers.  scaling = weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+IN_W, IN_H, RENDER_SCALE, SHARPNESS = 1683, 1869, 0.75, 0.9
+OUT_W, OUT_H = 2244, 2492
+EASU_BYTES_PER_EYE = IN_W * IN_H * 4 + OUT_W * OUT_H * 4          # 34,950,300
+RCAS_BYTES_PER_EYE = 2 * OUT_W * OUT_H * 4                          # 44,736,384
+PAIR_BYTES = 2 * (EASU_BYTES_PER_EYE + RCAS_BYTES_PER_EYE)          # 159,373,368
+METRIC = "stereo eye-pairs/sec EASU+RCAS @2244x2492"
+WORKLOAD = "C2: stereo 1683x1869->2244x2492 RGBA8, renderScale=0.75, sharpness=0.9, FSR EASU+RCAS"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline
+# ------------------------------------------------------------------------------------------------------
+def cpu_pair_seconds(left, right, radius, which, threads, reps=2):
+    """Time one stereo pair (EASU+RCAS, both eyes) on the host with `threads` threads; best of reps."""
+    from oracle import pyoracle as po
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for eye, img in ((0, left), (1, right)):
+            uc = po.upscale_constants(eye, True, IN_W, IN_H, OUT_W, OUT_H, radius=radius)
+            sc = po.sharpen_constants(eye, True, OUT_W, OUT_H, radius=radius, sharpness=SHARPNESS)
+            po.rcas(po.easu(img, OUT_W, OUT_H, uc, which=which, nthreads=threads), sc, which=which, nthreads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(radius, reps=2):
+    from oracle import pyoracle as po
+    from openvr_fsr_b200 import synth
+    which, kind = ("ref", "reference") if po.ref_available() else ("oracle", "port")
+    threads = os.cpu_count() or 1
+    left, right = synth.stereo_pair("natural", IN_W, IN_H, 1)
+    sec = cpu_pair_seconds(left, right, radius, which, threads, reps)
+    return {"value": 1.0 / sec, "unit": "pairs/s", "cores": threads, "kind": kind,
+            "sample": f"1 stereo pair of the same workload (both eyes EASU+RCAS), {threads} threads, best of {reps}"}, which
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    from openvr_fsr_b200 import synth
+    which, kind = ("ref", "reference") if po.ref_available() else ("oracle", "port")
+    threads = os.cpu_count() or 1
+    left, right = synth.stereo_pair("natural", IN_W, IN_H, 1)
+    for _ in range(min(args.warmup, 1)):
+        cpu_pair_seconds(left, right, args.radius, which, threads, 1)
+    steps = max(1, min(args.steps, 12))  # each step = 1 pair; bounded so the run ends within minutes
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pair_seconds(left, right, args.radius, which, threads, 1)
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    sample = f"{steps} steps x 1 stereo pair, {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "radius": args.radius, "pairs_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--radius", type=float, default=2.0, help="Config::radius; 2.0 = mask off (headline)")
+    ap.add_argument("--pool", type=int, default=8, help="distinct stereo pairs per GPU per step (pool > L2)")
+    ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import openvr_fsr_b200 as ovr
+    from openvr_fsr_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    math_mode = ovr.MATH_STRICT if args.math == "strict" else ovr.MATH_FAST
+    cfg = ovr.Config(fsrEnabled=True, renderScale=RENDER_SCALE, sharpness=SHARPNESS, radius=args.radius,
+                     mathMode=math_mode, device=local_rank)
+
+    # north_star: NCCL only as barrier / broadcast of the shared FSR constants (96 + 48 bytes), root 0
+    from openvr_fsr_b200 import sharding
+    consts = sharding.broadcast_constants(cfg, IN_W, IN_H, OUT_W, OUT_H, dev if world > 1 else None)
+
+    # per-rank input pool: POOL distinct stereo pairs, resident in HBM
+    pool = []
+    base_l, base_r = synth.stereo_pair("natural", IN_W, IN_H, 1)
+    for i in range(args.pool):
+        sh = 37 * (i + rank * args.pool)
+        pool.append((torch.from_numpy(np.roll(base_l, sh, axis=0)).to(dev),
+                     torch.from_numpy(np.roll(base_r, sh, axis=0)).to(dev)))
+    pp = ovr.PostProcessor(cfg)
+    assert np.array_equal(pp_consts_after_first(pp, pool[0][0]), consts["upscale"][0]), "rank constants differ from root's"
+
+    def step():
+        for left, right in pool:
+            pp.apply(ovr.EYE_LEFT, left)
+            pp.apply(ovr.EYE_RIGHT, right)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ovr.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = ovr.kernel_launches() - launches0
+    elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    pairs = world * args.pool * args.steps
+    value = pairs / (elapsed_ms * 1e-3)
+
+    # ---- instrumented pass: per-kernel CUDA events on the launch stream (roofline of the dominant kernel)
+    easu_ms, rcas_ms = per_kernel_times(ovr, pool, consts, math_mode, min(args.steps, 5))
+    peak, peak_src = _peaks()
+    easu_gbs = EASU_BYTES_PER_EYE / (easu_ms * 1e-3) / 1e9
+    rcas_gbs = RCAS_BYTES_PER_EYE / (rcas_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "easu_kernel", "achieved": easu_gbs, "peak": peak, "unit": "GB/s",
+                "frac": easu_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": EASU_BYTES_PER_EYE, "ms_per_launch": easu_ms,
+                "note": "EASU is FP32-issue-bound, not HBM-bound, when the mask is off (DESIGN.md section 5)"}
+    roofline_rcas = {"bound": "hbm", "kernel": "rcas_kernel", "achieved": rcas_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": rcas_gbs / peak, "algorithmic_bytes_per_launch": RCAS_BYTES_PER_EYE, "ms_per_launch": rcas_ms}
+
+    # ---- end to end: host buffers through the public API, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_run(ovr, torch, dist, cfg, pool, dev, world, max(2, args.steps // 4), args.warmup)
+
+    # ---- reference default radius beside the headline
+    masked = None
+    if args.radius != 0.5:
+        masked = quick_value(ovr, torch, cfg, pool, 0.5, max(3, args.steps // 2))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_baseline(args.radius)
+
+    pp.close()
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "radius": args.radius, "pairs_per_step_per_gpu": args.pool,
+                       "math": args.math, "l2": f"inputs larger than L2 ({args.pool} distinct pairs = "
+                       f"{args.pool * 2 * IN_W * IN_H * 4 / 1e6:.0f} MB per GPU per step)",
+                       "parallelism": f"frames sharded {world}x, no data-path collective"},
+            "hbm_gbs_whole_pass": value / world * PAIR_BYTES / 1e9,
+            "hbm_frac_whole_pass": value / world * PAIR_BYTES / 1e9 / peak,
+            "roofline": roofline, "roofline_rcas": roofline_rcas, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        if masked is not None:
+            out["masked_r0.5"] = {"value": masked * world, "unit": "pairs/s",
+                                  "note": "reference default radius 0.5 (EASU/RCAS inside the radius only)"}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def pp_consts_after_first(pp, tex):
+    import torch
+    pp.apply(0, tex)
+    torch.cuda.synchronize()
+    c = pp.upscale_constants(0)
+    pp.reset()
+    return c
+
+
+def per_kernel_times(ovr, pool, consts, math_mode, reps):
+    """Mean device time of one EASU and one RCAS launch (per eye), events recorded on the launching stream."""
+    import torch
+    dev = pool[0][0].device
+    mid = torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8, device=dev)
+    dst = torch.empty_like(mid)
+    te, tr = [], []
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for _ in range(reps):
+        for left, right in pool:
+            for eye, tex in ((0, left), (1, right)):
+                evs[0].record()
+                ovr.fsr_easu(tex, mid, consts["upscale"][eye], math_mode)
+                evs[1].record()
+                ovr.fsr_rcas(mid, dst, consts["sharpen"][eye], math_mode)
+                evs[2].record()
+                evs[2].synchronize()
+                te.append(evs[0].elapsed_time(evs[1]))
+                tr.append(evs[1].elapsed_time(evs[2]))
+    skip = min(len(te) // 4, 8)
+    return statistics.mean(te[skip:]), statistics.mean(tr[skip:])
+
+
+def quick_value(ovr, torch, cfg, pool, radius, steps):
+    import dataclasses
+    pp = ovr.PostProcessor(dataclasses.replace(cfg, radius=radius))
+    for _ in range(2):
+        for left, right in pool:
+            pp.apply(0, left); pp.apply(1, right)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        for left, right in pool:
+            pp.apply(0, left); pp.apply(1, right)
+    e1.record()
+    torch.cuda.synchronize()
+    v = len(pool) * steps / (e0.elapsed_time(e1) * 1e-3)
+    pp.close()
+    return v
+
+
+def e2e_run(ovr, torch, dist, cfg, pool, dev, world, steps, warmup):
+    """Same metric through the reference-facing call with HOST buffers: per eye, pinned host -> device copy,
+    EASU+RCAS, device -> pinned host copy, all inside the timed region.  Two streams (one per eye) so the two
+    copy engines and the SMs overlap."""
+    pp = ovr.PostProcessor(cfg)
+    n = len(pool)
+    h_in = [(l.cpu().pin_memory(), r.cpu().pin_memory()) for l, r in pool]
+    h_out = [(torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8).pin_memory(),
+              torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8).pin_memory()) for _ in range(n)]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+
+    def step():
+        for i in range(n):
+            for eye in (0, 1):
+                pp.apply_host(eye, h_in[i][eye], h_out[i][eye], stream=streams[eye])
+
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(streams[0])
+    for _ in range(steps):
+        step()
+    streams[0].wait_stream(streams[1])
+    e1.record(streams[0])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    pp.close()
+    pairs = world * n * steps
+    return {"value": pairs / (float(ms.item()) * 1e-3), "unit": "pairs/s",
+            "h2d_bytes_per_step": n * 2 * IN_W * IN_H * 4, "d2h_bytes_per_step": n * 2 * OUT_W * OUT_H * 4,
+            "steps": steps, "wall_value": pairs / world / wall * world,
+            "note": "pinned host -> H2D -> EASU+RCAS -> D2H per eye via ovrfsr_apply_host, 2 streams"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+/*
+ * ovrfsr.h -- C ABI of the B200-native FSR1 / NIS eye-texture post-process.
+ *
+ * This is the drop-in boundary for ONE path of fholger/openvr_fsr: the per-eye pass that
+ * vr::PostProcessor::Apply runs from the IVRCompositor::Submit hook
+ * (src/postprocess/PostProcessor.cpp:123-164, called from src/postprocess/VrHooks.cpp:53,71,84).
+ * Everything D3D11 did on that path (compute-shader dispatch of fsr_easu / fsr_rcas /
+ * NIS_Upscale / NIS_Sharpen, constant buffers, intermediate textures) is behind these calls
+ * as hand-written sm_100a CUDA kernels.  Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary.  All citations are relative to /root/reference/.
+ *
+ * The C++ class a maintainer links instead of the D3D11 one is
+ * openvr_fsr_b200/csrc/postprocessor.h (same Apply/Reset surface); INTEGRATION.md shows
+ * the binding.  There is NO CPU fallback: every entry point that launches work returns
+ * OVRFSR_ERR_CUDA if no sm_100 device / driver is usable.
+ */
+#ifndef OVRFSR_H
+#define OVRFSR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define OVRFSR_API __declspec(dllexport)
+#else
+#define OVRFSR_API __attribute__((visibility("default")))
+#endif
+
+#define OVRFSR_VERSION 0x00010000u
+
+/* status codes.  The reference's error convention is "log, disable, pass the frame through"
+ * (PostProcessor.cpp:23-28,145-152); the C++ wrapper maps any non-zero status to that. */
+typedef enum ovrfsr_status {
+  OVRFSR_OK = 0,
+  OVRFSR_ERR_INVALID = 1,     /* null / malformed argument */
+  OVRFSR_ERR_UNSUPPORTED = 2, /* format or scale the path does not handle */
+  OVRFSR_ERR_CUDA = 3,        /* CUDA runtime / driver failure, or no device */
+  OVRFSR_ERR_NOMEM = 4,
+  OVRFSR_PASSTHROUGH = 5      /* fsr_enabled == 0: nothing done, caller submits its own texture */
+} ovrfsr_status;
+
+/* pixel formats: the DXGI formats the path binds (PostProcessor.cpp:30-74) */
+typedef enum ovrfsr_format {
+  OVRFSR_FORMAT_RGBA8 = 0,   /* DXGI_FORMAT_R8G8B8A8_UNORM (sRGB variants are viewed as UNORM, :50-61) */
+  OVRFSR_FORMAT_BGRA8 = 1,   /* DXGI_FORMAT_B8G8R8A8_UNORM */
+  OVRFSR_FORMAT_RGBA16F = 2, /* DXGI_FORMAT_R16G16B16A16_FLOAT */
+  OVRFSR_FORMAT_AUTO = -1    /* output only: DetermineOutputFormat(), :63-74 -> RGBA8 */
+} ovrfsr_format;
+
+/* arithmetic mode of the kernels */
+typedef enum ovrfsr_math {
+  OVRFSR_MATH_FAST = 0,  /* FMA contraction + algebraically regrouped taps; <=1 LSB (RGBA8) vs the reference lines */
+  OVRFSR_MATH_STRICT = 1 /* the reference's operation order, no contraction: bit-identical to the reference lines */
+} ovrfsr_math;
+
+/* Device-resident image: the CUDA analogue of the ID3D11Texture2D* that Texture_t::handle
+ * carries (headers/openvr.h:177-182).  data is a device pointer unless stated otherwise. */
+typedef struct ovrfsr_image {
+  void *data;
+  uint32_t width;
+  uint32_t height;
+  uint32_t pitch;       /* bytes per row; rows need not be tightly packed */
+  int32_t format;       /* ovrfsr_format */
+  uint32_t array_slices;/* >1: right eye lives in slice 1 (PostProcessor.cpp:254-268); 0 is treated as 1 */
+  uint32_t slice_pitch; /* bytes between slices when array_slices > 1 */
+} ovrfsr_image;
+
+/* The Config fields that steer the path (src/postprocess/Config.h:11-17) plus what the
+ * reference pulls from the live runtime (projection centres, PostProcessor.cpp:104-121). */
+typedef struct ovrfsr_config {
+  uint32_t struct_size;   /* sizeof(ovrfsr_config) */
+  int32_t fsr_enabled;    /* Config::fsrEnabled */
+  int32_t use_nis;        /* Config::useNis */
+  float render_scale;     /* Config::renderScale */
+  float sharpness;        /* Config::sharpness */
+  float radius;           /* Config::radius */
+  int32_t debug_mode;     /* Config::debugMode: tints the outside-radius region, enables timing */
+  float proj_centre[4];   /* {leftX,leftY,rightX,rightY}; 0.5 each for a symmetric HMD */
+  int32_t device;         /* CUDA device ordinal, -1 = current device */
+  int32_t output_format;  /* ovrfsr_format, AUTO = reference behaviour */
+  int32_t math_mode;      /* ovrfsr_math */
+  int32_t reserved[5];
+} ovrfsr_config;
+
+typedef struct ovrfsr_ctx ovrfsr_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Fills cfg with the reference defaults (Config.h:11-17: enabled=false, renderScale=1,
+ * sharpness=0.75, radius=0.5) and proj centres 0.5. */
+OVRFSR_API void ovrfsr_config_default(ovrfsr_config *cfg);
+/* Replaces the `PostProcessor postProcessor;` global (VrHooks.cpp:19).  No GPU work happens here. */
+OVRFSR_API int ovrfsr_create(ovrfsr_ctx **out, const ovrfsr_config *cfg);
+OVRFSR_API void ovrfsr_destroy(ovrfsr_ctx *ctx);
+/* PostProcessor::Reset (PostProcessor.cpp:166-194): drops every cached resource, re-enables. */
+OVRFSR_API int ovrfsr_reset(ovrfsr_ctx *ctx);
+/* What the hotkeys do (PostProcessor.cpp:670-704): mutate Config, then Reset. */
+OVRFSR_API int ovrfsr_set_config(ovrfsr_ctx *ctx, const ovrfsr_config *cfg);
+OVRFSR_API int ovrfsr_get_config(const ovrfsr_ctx *ctx, ovrfsr_config *cfg);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* PostProcessor::Apply minus the OpenVR types (PostProcessor.cpp:123-164,563-638).
+ *   eye           EVREye (0 left, 1 right)
+ *   src           borrowed, read-only
+ *   only_one_eye  |uMax-uMin| > .5 of the submit bounds (:146); 0 = both eyes side by side in src
+ *   out           receives the ctx-owned output image (upscaled+sharpened); valid until the next
+ *                 apply for the same eye, reset or destroy.  One output per eye (the reference
+ *                 shares one between both eyes, PostProcessor.h:43,58).
+ *   stream        cudaStream_t; work is enqueued asynchronously, nothing is synchronised.
+ * Lazy-initialises on first call and re-initialises when src dimensions change (:136-143).
+ * Pass selection: upscale iff renderScale != 1; sharpen iff !useNis || renderScale == 1 (:586-594). */
+OVRFSR_API int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src, int only_one_eye,
+                            ovrfsr_image *out, void *stream);
+/* Same pass with HOST images: copies src host->device, runs ovrfsr_apply, copies the result to
+ * dst_host (which must be outW x outH of the ctx output format), all on `stream`.  Pinned host
+ * memory makes the copies asynchronous.  This is the end-to-end entry bench.py times. */
+OVRFSR_API int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, int only_one_eye,
+                                 const ovrfsr_image *dst_host, void *stream);
+
+/* ---- individual dispatches (ApplyUpscaling / ApplySharpening, PostProcessor.cpp:385-401,483-496) --
+ * Stateless: explicit constant blocks, caller-owned destination.  math_mode as ovrfsr_math. */
+/* g_FSRUpscaleShader: consts = UpscaleConstants, 24 x u32 (PostProcessor.cpp:276-283) */
+OVRFSR_API int ovrfsr_dispatch_fsr_easu(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[24],
+                                        int math_mode, void *stream);
+/* g_FSRSharpenShader: consts = SharpenConstants, 12 x u32 (PostProcessor.cpp:403-407) */
+OVRFSR_API int ovrfsr_dispatch_fsr_rcas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[12],
+                                        int math_mode, void *stream);
+/* g_NISUpscaleShader / g_NISSharpenShader: cfg = NISConfig, 256 bytes (NIS_Config.h:37-77 + the
+ * mod's centre/radius at byte 112, PostProcessor.cpp:310) */
+OVRFSR_API int ovrfsr_dispatch_nis_scaler(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256,
+                                          int math_mode, void *stream);
+OVRFSR_API int ovrfsr_dispatch_nis_sharpen(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256,
+                                           int math_mode, void *stream);
+
+/* ---- host-side constant setup (pure CPU; usable without a GPU) -------------------------- */
+/* PrepareResources, PostProcessor.cpp:509-518 */
+OVRFSR_API void ovrfsr_output_size(uint32_t in_w, uint32_t in_h, float render_scale, uint32_t *out_w,
+                                   uint32_t *out_h);
+/* FsrEasuCon, ffx_fsr1.h:156-202 */
+OVRFSR_API void ovrfsr_fsr_easu_con(uint32_t con[16], float in_vp_w, float in_vp_h, float in_w, float in_h,
+                                    float out_w, float out_h);
+/* FsrRcasCon, ffx_fsr1.h:662-672 (argument in stops) */
+OVRFSR_API void ovrfsr_fsr_rcas_con(uint32_t con[4], float sharpness_stops);
+/* UpscaleConstants for one eye, PostProcessor.cpp:293-305,331-337 */
+OVRFSR_API void ovrfsr_make_upscale_constants(uint32_t consts[24], const ovrfsr_config *cfg, int eye,
+                                              int only_one_eye, uint32_t in_w, uint32_t in_h, uint32_t out_w,
+                                              uint32_t out_h);
+/* SharpenConstants for one eye, PostProcessor.cpp:416-430,453-459 */
+OVRFSR_API void ovrfsr_make_sharpen_constants(uint32_t consts[12], const ovrfsr_config *cfg, int eye,
+                                              int only_one_eye, uint32_t out_w, uint32_t out_h);
+/* NISConfig for one eye: NVScalerUpdateConfig (sharpen_only=0, PostProcessor.cpp:307-310) or
+ * NVSharpenUpdateConfig (sharpen_only=1, :432-435).  Returns the bool the mod ignores (1 = scale in range). */
+OVRFSR_API int ovrfsr_make_nis_config(void *cfg256, const ovrfsr_config *cfg, int sharpen_only, int eye,
+                                      int only_one_eye, uint32_t in_w, uint32_t in_h, uint32_t out_w,
+                                      uint32_t out_h);
+/* coef_scale / coef_usm, NIS_Config.h:261-393: 64 phases x 8 floats */
+OVRFSR_API const float *ovrfsr_nis_coef_scale(void);
+OVRFSR_API const float *ovrfsr_nis_coef_usm(void);
+
+/* ---- introspection -------------------------------------------------------------------- */
+/* constant blocks the ctx built for `eye` (valid after the first apply) */
+OVRFSR_API int ovrfsr_get_upscale_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts[24]);
+OVRFSR_API int ovrfsr_get_sharpen_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts[12]);
+/* kernels launched by this library in this process since load (bench.py's gpu_launches) */
+OVRFSR_API uint64_t ovrfsr_kernel_launches(void);
+/* debugMode profiling (PostProcessor.cpp:547-557,601-628): mean GPU ms per apply over the samples
+ * collected so far (cudaEvent pairs read back a few frames late); returns samples used, 0 if none. */
+OVRFSR_API int ovrfsr_get_gpu_time_ms(ovrfsr_ctx *ctx, float *mean_ms);
+OVRFSR_API const char *ovrfsr_last_error(const ovrfsr_ctx *ctx);
+OVRFSR_API const char *ovrfsr_status_string(int status);
+OVRFSR_API uint32_t ovrfsr_version(void);
+/* device image helpers (cudaMalloc with a 256-byte-aligned pitch, cudaFree) */
+OVRFSR_API int ovrfsr_image_alloc(ovrfsr_image *img, uint32_t width, uint32_t height, int32_t format);
+OVRFSR_API void ovrfsr_image_free(ovrfsr_image *img);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVRFSR_H */

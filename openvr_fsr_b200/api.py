@@ -1,0 +1,215 @@
+"""Python mirror of the reference's post-process surface, over the C ABI.
+
+`PostProcessor.apply / reset` keep the names and argument meaning of vr::PostProcessor::Apply / Reset
+(/root/reference/src/postprocess/PostProcessor.h:12-13); `Config` carries the fields of the reference's
+Config singleton that steer this path (src/postprocess/Config.h:11-17).  Images are torch CUDA tensors
+(H, W, 4) uint8 or float16 -- torch only provides device memory and streams here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class Config:
+    """src/postprocess/Config.h:11-17 plus the projection centres the reference reads from IVRSystem."""
+    fsrEnabled: bool = False
+    useNis: bool = False
+    renderScale: float = 1.0
+    sharpness: float = 0.75
+    radius: float = 0.5
+    debugMode: bool = False
+    projCentre: tuple = (0.5, 0.5, 0.5, 0.5)
+    device: int = -1
+    outputFormat: int = L.FORMAT_AUTO
+    mathMode: int = L.MATH_FAST
+
+    def to_c(self) -> L.Config:
+        c = L.Config()
+        L.lib().ovrfsr_config_default(C.byref(c))
+        c.fsr_enabled, c.use_nis = int(self.fsrEnabled), int(self.useNis)
+        c.render_scale, c.sharpness, c.radius = self.renderScale, self.sharpness, self.radius
+        c.debug_mode = int(self.debugMode)
+        c.proj_centre = (C.c_float * 4)(*self.projCentre)
+        c.device, c.output_format, c.math_mode = self.device, self.outputFormat, self.mathMode
+        return c
+
+
+@dataclass
+class TextureBounds:
+    """VRTextureBounds_t, headers/openvr.h:609-613"""
+    uMin: float = 0.0
+    vMin: float = 0.0
+    uMax: float = 1.0
+    vMax: float = 1.0
+
+
+EYE_LEFT, EYE_RIGHT = 0, 1
+
+
+def _format_of(t) -> int:
+    import torch
+    if t.dtype == torch.uint8:
+        return L.FORMAT_RGBA8
+    if t.dtype == torch.float16:
+        return L.FORMAT_RGBA16F
+    raise TypeError("eye textures are uint8 (RGBA8/BGRA8) or float16 (RGBA16F) tensors of shape (H, W, 4)")
+
+
+def image_of(t, fmt: int | None = None) -> L.Image:
+    """Describe a (H, W, 4) tensor (CUDA or pinned host) as an ovrfsr_image; rows may be strided."""
+    if t.dim() != 3 or t.shape[2] != 4 or t.stride(2) != 1 or t.stride(1) != 4:
+        raise ValueError("expected a (H, W, 4) tensor with packed pixels")
+    return L.Image(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0) * t.element_size(),
+                   _format_of(t) if fmt is None else fmt, 1, 0)
+
+
+def output_size(in_w: int, in_h: int, render_scale: float) -> tuple[int, int]:
+    """PrepareResources, PostProcessor.cpp:509-518"""
+    w, h = C.c_uint32(), C.c_uint32()
+    L.lib().ovrfsr_output_size(in_w, in_h, render_scale, C.byref(w), C.byref(h))
+    return w.value, h.value
+
+
+def _stream_ptr(stream) -> int:
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return s.cuda_stream
+
+
+class PostProcessor:
+    """Drop-in for vr::PostProcessor on this path: apply(eye, texture, bounds) returns the texture the hook
+    would hand on to the real Submit (the ctx-owned upscaled/sharpened eye), or the input itself when
+    post-processing is disabled -- the reference's pass-through behaviour (PostProcessor.cpp:124,145-152)."""
+
+    def __init__(self, config: Config):
+        self._ctx = C.c_void_p()
+        self.config = config
+        L.check(L.lib().ovrfsr_create(C.byref(self._ctx), C.byref(config.to_c())), "ovrfsr_create")
+
+    def close(self):
+        if self._ctx:
+            L.lib().ovrfsr_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def reset(self):
+        """vr::PostProcessor::Reset"""
+        L.check(L.lib().ovrfsr_reset(self._ctx), "ovrfsr_reset", self._ctx)
+
+    def set_config(self, config: Config):
+        """What the hotkeys do: mutate Config, then Reset (PostProcessor.cpp:670-704)."""
+        self.config = config
+        L.check(L.lib().ovrfsr_set_config(self._ctx, C.byref(config.to_c())), "ovrfsr_set_config", self._ctx)
+
+    def apply(self, eye: int, texture, bounds: TextureBounds | None = None, fmt: int | None = None, stream=None):
+        """vr::PostProcessor::Apply.  Returns a torch tensor VIEW of the ctx-owned output (valid until the next
+        apply for this eye / reset), or `texture` itself on pass-through."""
+        import torch
+        bounds = bounds or TextureBounds()
+        only_one_eye = int(abs(bounds.uMax - bounds.uMin) > 0.5)  # PostProcessor.cpp:146
+        src, out = image_of(texture, fmt), L.Image()
+        rc = L.lib().ovrfsr_apply(self._ctx, eye, C.byref(src), only_one_eye, C.byref(out), _stream_ptr(stream))
+        if rc == L.PASSTHROUGH:
+            return texture
+        L.check(rc, "ovrfsr_apply", self._ctx)
+        return _wrap_device(out, texture.device)
+
+    def apply_host(self, eye: int, src_host, dst_host, bounds: TextureBounds | None = None, fmt: int | None = None,
+                   stream=None):
+        """End-to-end entry: host (pinned) tensors in and out, copies included, asynchronous on `stream`."""
+        bounds = bounds or TextureBounds()
+        only_one_eye = int(abs(bounds.uMax - bounds.uMin) > 0.5)
+        s, d = image_of(src_host, fmt), image_of(dst_host)
+        L.check(L.lib().ovrfsr_apply_host(self._ctx, eye, C.byref(s), only_one_eye, C.byref(d), _stream_ptr(stream)),
+                "ovrfsr_apply_host", self._ctx)
+
+    def upscale_constants(self, eye: int) -> np.ndarray:
+        w = (C.c_uint32 * 24)()
+        L.check(L.lib().ovrfsr_get_upscale_constants(self._ctx, eye, w), "get_upscale_constants")
+        return np.array(w, dtype=np.uint32)
+
+    def sharpen_constants(self, eye: int) -> np.ndarray:
+        w = (C.c_uint32 * 12)()
+        L.check(L.lib().ovrfsr_get_sharpen_constants(self._ctx, eye, w), "get_sharpen_constants")
+        return np.array(w, dtype=np.uint32)
+
+    def gpu_time_ms(self):
+        ms = C.c_float()
+        n = L.lib().ovrfsr_get_gpu_time_ms(self._ctx, C.byref(ms))
+        return (ms.value, n) if n else (None, 0)
+
+
+def _wrap_device(img: L.Image, device):
+    """torch view over a ctx-owned device image (no copy)."""
+    import torch
+    elem = 2 if img.format == L.FORMAT_RGBA16F else 1
+    dtype = torch.float16 if img.format == L.FORMAT_RGBA16F else torch.uint8
+    nbytes = img.pitch * img.height
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (img.data, False), "version": 2}
+    flat = torch.as_tensor(h, device=device)
+    rows = flat.view(img.height, img.pitch)[:, : img.width * 4 * elem]
+    if elem == 2:
+        return torch.as_strided(flat.view(torch.float16), (img.height, img.width, 4), (img.pitch // 2, 4, 1))
+    return torch.as_strided(flat, (img.height, img.width, 4), (img.pitch, 4, 1))
+
+
+# ---- the individual dispatches (ApplyUpscaling / ApplySharpening) on tensors ---------------------------
+def _dispatch(fn, src, dst, consts, math_mode, stream, src_fmt=None):
+    s, d = image_of(src, src_fmt), image_of(dst)
+    L.check(fn(C.byref(s), C.byref(d), consts, math_mode, _stream_ptr(stream)), fn.__name__)
+    return dst
+
+
+def fsr_easu(src, dst, consts24, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+    c = (C.c_uint32 * 24)(*[int(x) for x in consts24])
+    return _dispatch(L.lib().ovrfsr_dispatch_fsr_easu, src, dst, c, math_mode, stream, src_fmt)
+
+
+def fsr_rcas(src, dst, consts12, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+    c = (C.c_uint32 * 12)(*[int(x) for x in consts12])
+    return _dispatch(L.lib().ovrfsr_dispatch_fsr_rcas, src, dst, c, math_mode, stream, src_fmt)
+
+
+def nis_scaler(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+    buf = C.create_string_buffer(bytes(cfg256), 256)
+    return _dispatch(L.lib().ovrfsr_dispatch_nis_scaler, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt)
+
+
+def nis_sharpen(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+    buf = C.create_string_buffer(bytes(cfg256), 256)
+    return _dispatch(L.lib().ovrfsr_dispatch_nis_sharpen, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt)
+
+
+def make_upscale_constants(cfg: Config, eye, only_one_eye, in_w, in_h, out_w, out_h) -> np.ndarray:
+    w = (C.c_uint32 * 24)()
+    L.lib().ovrfsr_make_upscale_constants(w, C.byref(cfg.to_c()), eye, int(only_one_eye), in_w, in_h, out_w, out_h)
+    return np.array(w, dtype=np.uint32)
+
+
+def make_sharpen_constants(cfg: Config, eye, only_one_eye, out_w, out_h) -> np.ndarray:
+    w = (C.c_uint32 * 12)()
+    L.lib().ovrfsr_make_sharpen_constants(w, C.byref(cfg.to_c()), eye, int(only_one_eye), out_w, out_h)
+    return np.array(w, dtype=np.uint32)
+
+
+def make_nis_config(cfg: Config, sharpen_only, eye, only_one_eye, in_w, in_h, out_w, out_h):
+    buf = C.create_string_buffer(256)
+    ok = L.lib().ovrfsr_make_nis_config(C.cast(buf, C.c_void_p), C.byref(cfg.to_c()), int(sharpen_only), eye,
+                                        int(only_one_eye), in_w, in_h, out_w, out_h)
+    return buf.raw, bool(ok)
+
+
+def kernel_launches() -> int:
+    return int(L.lib().ovrfsr_kernel_launches())

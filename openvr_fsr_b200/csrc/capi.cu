@@ -1,0 +1,460 @@
+// capi.cu -- implementation of include/ovrfsr.h: the state machine of vr::PostProcessor
+// (src/postprocess/PostProcessor.cpp:123-194,498-638 in /root/reference) over CUDA resources,
+// plus the stateless per-dispatch entry points.  No CPU fallback exists: if CUDA is unusable the
+// calls fail with OVRFSR_ERR_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "host_constants.h"
+#include "kernels.h"
+
+namespace ovrfsr {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+} // namespace ovrfsr
+
+using namespace ovrfsr;
+
+namespace {
+
+constexpr int kQueryCount = 6; // QUERY_COUNT, PostProcessor.h:78
+
+inline uint32_t bytes_per_pixel(int fmt) { return fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u; }
+inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGBA16F; }
+inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+struct DeviceImage {
+  ovrfsr_image img{};
+  bool alloc(uint32_t w, uint32_t h, int fmt) {
+    release();
+    img.width = w; img.height = h; img.format = fmt; img.array_slices = 1; img.slice_pitch = 0;
+    img.pitch = align_up(w * bytes_per_pixel(fmt), 256u);
+    return cudaMalloc(&img.data, (size_t)img.pitch * h) == cudaSuccess;
+  }
+  void release() {
+    if (img.data) cudaFree(img.data);
+    img = ovrfsr_image{};
+  }
+};
+
+PassImage pass_image(const ovrfsr_image &im, int slice = 0) {
+  PassImage p;
+  p.ptr = static_cast<uint8_t *>(im.data) + (size_t)slice * im.slice_pitch;
+  p.pitch = im.pitch; p.w = (int)im.width; p.h = (int)im.height; p.format = im.format;
+  return p;
+}
+
+} // namespace
+
+struct ovrfsr_ctx {
+  ovrfsr_config cfg{};
+  // PostProcessor.h:16-24
+  bool enabled = true;
+  bool initialized = false;
+  uint32_t inputWidth = 0, inputHeight = 0, outputWidth = 0, outputHeight = 0;
+  bool textureContainsOnlyOneEye = true;
+  int outFormat = OVRFSR_FORMAT_RGBA8;
+  int inFormat = OVRFSR_FORMAT_RGBA8;
+  // per-eye constant blocks (upscaleConstantsBuffer[2] / sharpenConstantsBuffer[2], PostProcessor.h:41,56)
+  uint32_t upscaleConstants[2][24]{};
+  uint32_t sharpenConstants[2][12]{};
+  alignas(16) uint8_t nisScalerConfig[2][256]{};
+  alignas(16) uint8_t nisSharpenConfig[2][256]{};
+  // one set of intermediates/outputs PER EYE (the reference shares one; see ovrfsr.h)
+  DeviceImage upscaled[2], sharpened[2];
+  DeviceImage hostStage[2]; // device staging of host-submitted eyes (ovrfsr_apply_host)
+  const void *lastSubmittedTexture = nullptr;
+  ovrfsr_image lastOutput{};
+  int eyeCount = 0;
+  // debugMode profiling ring (PostProcessor.h:72-82)
+  cudaEvent_t evStart[kQueryCount]{}, evEnd[kQueryCount]{};
+  bool evPending[kQueryCount]{};
+  bool evCreated = false;
+  int currentQuery = 0;
+  float summedGpuTime = 0.f;
+  int countedQueries = 0;
+  std::string lastError;
+};
+
+namespace {
+
+int fail(ovrfsr_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    ctx->lastError = what;
+    if (e != cudaSuccess) { ctx->lastError += ": "; ctx->lastError += cudaGetErrorString(e); }
+  }
+  return status;
+}
+
+void release_resources(ovrfsr_ctx *c) {
+  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); }
+  if (c->evCreated) {
+    for (int i = 0; i < kQueryCount; ++i) { cudaEventDestroy(c->evStart[i]); cudaEventDestroy(c->evEnd[i]); c->evPending[i] = false; }
+    c->evCreated = false;
+  }
+}
+
+int select_device(ovrfsr_ctx *c) {
+  if (c->cfg.device >= 0) {
+    cudaError_t e = cudaSetDevice(c->cfg.device);
+    if (e != cudaSuccess) return fail(c, OVRFSR_ERR_CUDA, "cudaSetDevice", e);
+  }
+  return OVRFSR_OK;
+}
+
+bool upscale_pass(const ovrfsr_config &cfg) { return cfg.render_scale != 1.f; }                    // PostProcessor.cpp:586
+bool sharpen_pass(const ovrfsr_config &cfg) { return !cfg.use_nis || cfg.render_scale == 1.f; }    // PostProcessor.cpp:591
+
+// PostProcessor::PrepareResources, PostProcessor.cpp:498-561
+int prepare_resources(ovrfsr_ctx *c, const ovrfsr_image *src) {
+  c->inputWidth = src->width;
+  c->inputHeight = src->height;
+  c->inFormat = src->format;
+  host::output_size(src->width, src->height, c->cfg.render_scale, &c->outputWidth, &c->outputHeight);
+  if (c->outputWidth == 0 || c->outputHeight == 0) return fail(c, OVRFSR_ERR_INVALID, "output size is zero");
+  // DetermineOutputFormat (PostProcessor.cpp:63-74): RGBA8 unless the caller asks for the FP16 extension
+  c->outFormat = c->cfg.output_format == OVRFSR_FORMAT_AUTO ? OVRFSR_FORMAT_RGBA8 : c->cfg.output_format;
+  if (c->outFormat != OVRFSR_FORMAT_RGBA8 && c->outFormat != OVRFSR_FORMAT_RGBA16F)
+    return fail(c, OVRFSR_ERR_UNSUPPORTED, "output format must be RGBA8 or RGBA16F");
+  const bool one = c->textureContainsOnlyOneEye;
+  const int neyes = one ? 2 : 1;
+  for (int e = 0; e < neyes; ++e) {
+    host::make_upscale_constants(c->upscaleConstants[e], c->cfg, e, one, c->inputWidth, c->inputHeight, c->outputWidth,
+                                 c->outputHeight);
+    host::make_sharpen_constants(c->sharpenConstants[e], c->cfg, e, one, c->outputWidth, c->outputHeight);
+    ovrfsr_make_nis_config(c->nisScalerConfig[e], &c->cfg, 0, e, one, c->inputWidth, c->inputHeight, c->outputWidth,
+                           c->outputHeight);
+    ovrfsr_make_nis_config(c->nisSharpenConfig[e], &c->cfg, 1, e, one, c->inputWidth, c->inputHeight, c->outputWidth,
+                           c->outputHeight);
+    if (upscale_pass(c->cfg) && !c->upscaled[e].alloc(c->outputWidth, c->outputHeight, c->outFormat))
+      return fail(c, OVRFSR_ERR_NOMEM, "allocating upscaled texture", cudaGetLastError());
+    if (sharpen_pass(c->cfg) && !c->sharpened[e].alloc(c->outputWidth, c->outputHeight, c->outFormat))
+      return fail(c, OVRFSR_ERR_NOMEM, "allocating sharpened texture", cudaGetLastError());
+  }
+  if (c->cfg.debug_mode) {
+    for (int i = 0; i < kQueryCount; ++i) {
+      if (cudaEventCreate(&c->evStart[i]) != cudaSuccess || cudaEventCreate(&c->evEnd[i]) != cudaSuccess)
+        return fail(c, OVRFSR_ERR_CUDA, "creating profiling events", cudaGetLastError());
+      c->evPending[i] = false;
+    }
+    c->evCreated = true;
+  }
+  c->initialized = true;
+  return OVRFSR_OK;
+}
+
+// harvest finished profiling samples (the GetData loop of PostProcessor.cpp:601-628, non-blocking)
+void harvest_queries(ovrfsr_ctx *c) {
+  if (!c->evCreated) return;
+  for (int i = 0; i < kQueryCount; ++i) {
+    if (!c->evPending[i] || cudaEventQuery(c->evEnd[i]) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->evStart[i], c->evEnd[i]) == cudaSuccess) { c->summedGpuTime += ms; ++c->countedQueries; }
+    c->evPending[i] = false;
+  }
+}
+
+int run_upscale(ovrfsr_ctx *c, int eye, const PassImage &in, const PassImage &out, cudaStream_t s) {
+  const bool strict = c->cfg.math_mode == OVRFSR_MATH_STRICT;
+  cudaError_t e;
+  if (c->cfg.use_nis) {
+    ovrfsr_image si{in.ptr, (uint32_t)in.w, (uint32_t)in.h, in.pitch, in.format, 1, 0};
+    ovrfsr_image di{out.ptr, (uint32_t)out.w, (uint32_t)out.h, out.pitch, out.format, 1, 0};
+    int rc = ovrfsr_dispatch_nis_scaler(&si, &di, c->nisScalerConfig[eye], c->cfg.math_mode, s);
+    return rc == OVRFSR_OK ? rc : fail(c, rc, "NIS scaler dispatch");
+  }
+  e = strict ? launch_easu_strict(in, out, c->upscaleConstants[eye], s) : launch_easu_fast(in, out, c->upscaleConstants[eye], s);
+  return e == cudaSuccess ? OVRFSR_OK : fail(c, OVRFSR_ERR_CUDA, "EASU launch", e);
+}
+
+int run_sharpen(ovrfsr_ctx *c, int eye, const PassImage &in, const PassImage &out, cudaStream_t s) {
+  const bool strict = c->cfg.math_mode == OVRFSR_MATH_STRICT;
+  if (c->cfg.use_nis) {
+    ovrfsr_image si{in.ptr, (uint32_t)in.w, (uint32_t)in.h, in.pitch, in.format, 1, 0};
+    ovrfsr_image di{out.ptr, (uint32_t)out.w, (uint32_t)out.h, out.pitch, out.format, 1, 0};
+    int rc = ovrfsr_dispatch_nis_sharpen(&si, &di, c->nisSharpenConfig[eye], c->cfg.math_mode, s);
+    return rc == OVRFSR_OK ? rc : fail(c, rc, "NIS sharpen dispatch");
+  }
+  cudaError_t e = strict ? launch_rcas_strict(in, out, c->sharpenConstants[eye], s)
+                         : launch_rcas_fast(in, out, c->sharpenConstants[eye], s);
+  return e == cudaSuccess ? OVRFSR_OK : fail(c, OVRFSR_ERR_CUDA, "RCAS launch", e);
+}
+
+// PostProcessor::ApplyPostProcess, PostProcessor.cpp:563-638 (binding save/restore, hotkeys and the
+// DDS capture belong to the D3D11/Win32 side and stay in the caller)
+int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_image *out, cudaStream_t s) {
+  // GetInputView: array textures keep the right eye in slice 1 (PostProcessor.cpp:254-268)
+  const int slice = (src->array_slices > 1 && eye == 1) ? 1 : 0;
+  PassImage in = pass_image(*src, slice);
+  ovrfsr_image result = *src;
+  int q = -1;
+  if (c->evCreated) {
+    harvest_queries(c);
+    q = c->currentQuery;
+    c->currentQuery = (c->currentQuery + 1) % kQueryCount;
+    if (c->evPending[q]) q = -1; // oldest sample still in flight: skip this frame rather than block
+    else cudaEventRecord(c->evStart[q], s);
+  }
+  if (upscale_pass(c->cfg)) {
+    int rc = run_upscale(c, eye, in, pass_image(c->upscaled[eye].img), s);
+    if (rc != OVRFSR_OK) return rc;
+    in = pass_image(c->upscaled[eye].img);
+    result = c->upscaled[eye].img;
+  }
+  if (sharpen_pass(c->cfg)) {
+    int rc = run_sharpen(c, eye, in, pass_image(c->sharpened[eye].img), s);
+    if (rc != OVRFSR_OK) return rc;
+    result = c->sharpened[eye].img;
+  }
+  if (q >= 0) { cudaEventRecord(c->evEnd[q], s); c->evPending[q] = true; }
+  *out = result;
+  return OVRFSR_OK;
+}
+
+int validate_image(const ovrfsr_image *im) {
+  if (!im || !im->data || im->width == 0 || im->height == 0) return OVRFSR_ERR_INVALID;
+  if (!valid_format(im->format)) return OVRFSR_ERR_UNSUPPORTED;
+  if (im->pitch < im->width * bytes_per_pixel(im->format) || (im->pitch % bytes_per_pixel(im->format)) != 0)
+    return OVRFSR_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(im->data) % bytes_per_pixel(im->format)) != 0) return OVRFSR_ERR_INVALID;
+  return OVRFSR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void ovrfsr_config_default(ovrfsr_config *cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = sizeof(ovrfsr_config);
+  cfg->fsr_enabled = 0;   // Config.h:11
+  cfg->use_nis = 0;       // Config.h:17
+  cfg->render_scale = 1.f;
+  cfg->sharpness = 0.75f;
+  cfg->radius = 0.5f;
+  cfg->debug_mode = 0;
+  cfg->proj_centre[0] = cfg->proj_centre[1] = cfg->proj_centre[2] = cfg->proj_centre[3] = 0.5f;
+  cfg->device = -1;
+  cfg->output_format = OVRFSR_FORMAT_AUTO;
+  cfg->math_mode = OVRFSR_MATH_FAST;
+}
+
+int ovrfsr_create(ovrfsr_ctx **out, const ovrfsr_config *cfg) {
+  if (!out || !cfg || cfg->struct_size != sizeof(ovrfsr_config)) return OVRFSR_ERR_INVALID;
+  if (!(cfg->render_scale > 0.f)) return OVRFSR_ERR_INVALID;
+  ovrfsr_ctx *c = new (std::nothrow) ovrfsr_ctx();
+  if (!c) return OVRFSR_ERR_NOMEM;
+  c->cfg = *cfg;
+  *out = c;
+  return OVRFSR_OK;
+}
+
+void ovrfsr_destroy(ovrfsr_ctx *ctx) {
+  if (!ctx) return;
+  if (ctx->initialized || ctx->hostStage[0].img.data || ctx->hostStage[1].img.data) {
+    if (ctx->cfg.device >= 0) cudaSetDevice(ctx->cfg.device);
+    release_resources(ctx);
+  }
+  delete ctx;
+}
+
+int ovrfsr_reset(ovrfsr_ctx *ctx) {
+  if (!ctx) return OVRFSR_ERR_INVALID;
+  if (ctx->initialized) {
+    if (ctx->cfg.device >= 0) cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize(); // outputs may still be in flight on the caller's stream
+    release_resources(ctx);
+  }
+  ctx->enabled = true;
+  ctx->initialized = false;
+  ctx->lastSubmittedTexture = nullptr;
+  ctx->lastOutput = ovrfsr_image{};
+  ctx->eyeCount = 0;
+  ctx->currentQuery = 0;
+  ctx->summedGpuTime = 0.f;
+  ctx->countedQueries = 0;
+  return OVRFSR_OK;
+}
+
+int ovrfsr_set_config(ovrfsr_ctx *ctx, const ovrfsr_config *cfg) {
+  if (!ctx || !cfg || cfg->struct_size != sizeof(ovrfsr_config) || !(cfg->render_scale > 0.f)) return OVRFSR_ERR_INVALID;
+  int rc = ovrfsr_reset(ctx);
+  ctx->cfg = *cfg;
+  return rc;
+}
+
+int ovrfsr_get_config(const ovrfsr_ctx *ctx, ovrfsr_config *cfg) {
+  if (!ctx || !cfg) return OVRFSR_ERR_INVALID;
+  *cfg = ctx->cfg;
+  return OVRFSR_OK;
+}
+
+int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src, int only_one_eye, ovrfsr_image *out, void *stream) {
+  if (!ctx || !out || (eye != 0 && eye != 1)) return OVRFSR_ERR_INVALID;
+  // PostProcessor.cpp:124: disabled or unusable texture -> the frame passes through untouched
+  if (!ctx->enabled || !ctx->cfg.fsr_enabled) return OVRFSR_PASSTHROUGH;
+  int rc = validate_image(src);
+  if (rc != OVRFSR_OK) return fail(ctx, rc, "invalid source image");
+  if ((rc = select_device(ctx)) != OVRFSR_OK) return rc;
+  if (ctx->initialized && (src->width != ctx->inputWidth || src->height != ctx->inputHeight || src->format != ctx->inFormat)) {
+    ovrfsr_reset(ctx); // "Texture size changed, recreating resources", PostProcessor.cpp:139-142
+  }
+  if (!ctx->initialized) {
+    ctx->textureContainsOnlyOneEye = only_one_eye != 0; // PostProcessor.cpp:146
+    rc = prepare_resources(ctx, src);
+    if (rc != OVRFSR_OK) { // PostProcessor.cpp:148-152: "Resource creation failed, disabling"
+      release_resources(ctx);
+      ctx->enabled = false;
+      return rc;
+    }
+  }
+  // a single shared texture for both eyes is processed on the first Submit only (PostProcessor.cpp:155-160)
+  if (ctx->eyeCount == 0 || ctx->textureContainsOnlyOneEye || src->data != ctx->lastSubmittedTexture) {
+    rc = apply_post_process(ctx, ctx->textureContainsOnlyOneEye ? eye : 0, src, &ctx->lastOutput,
+                            static_cast<cudaStream_t>(stream));
+    if (rc != OVRFSR_OK) return rc;
+  }
+  ctx->lastSubmittedTexture = src->data;
+  ctx->eyeCount = (ctx->eyeCount + 1) % 2;
+  *out = ctx->lastOutput;
+  return OVRFSR_OK;
+}
+
+int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, int only_one_eye,
+                      const ovrfsr_image *dst_host, void *stream) {
+  if (!ctx || (eye != 0 && eye != 1)) return OVRFSR_ERR_INVALID;
+  if (!ctx->enabled || !ctx->cfg.fsr_enabled) return OVRFSR_PASSTHROUGH;
+  int rc = validate_image(src_host);
+  if (rc != OVRFSR_OK) return fail(ctx, rc, "invalid host source image");
+  if ((rc = validate_image(dst_host)) != OVRFSR_OK) return fail(ctx, rc, "invalid host destination image");
+  if ((rc = select_device(ctx)) != OVRFSR_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DeviceImage &st = ctx->hostStage[eye];
+  if (!st.img.data || st.img.width != src_host->width || st.img.height != src_host->height || st.img.format != src_host->format) {
+    if (!st.alloc(src_host->width, src_host->height, src_host->format))
+      return fail(ctx, OVRFSR_ERR_NOMEM, "allocating host staging image", cudaGetLastError());
+  }
+  const size_t rowBytes = (size_t)src_host->width * bytes_per_pixel(src_host->format);
+  cudaError_t e = cudaMemcpy2DAsync(st.img.data, st.img.pitch, src_host->data, src_host->pitch, rowBytes, src_host->height,
+                                    cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return fail(ctx, OVRFSR_ERR_CUDA, "host->device copy", e);
+  ovrfsr_image out{};
+  rc = ovrfsr_apply(ctx, eye, &st.img, only_one_eye, &out, stream);
+  if (rc != OVRFSR_OK) return rc;
+  if (dst_host->width != out.width || dst_host->height != out.height || dst_host->format != out.format)
+    return fail(ctx, OVRFSR_ERR_INVALID, "host destination does not match the output size/format");
+  e = cudaMemcpy2DAsync(dst_host->data, dst_host->pitch, out.data, out.pitch, (size_t)out.width * bytes_per_pixel(out.format),
+                        out.height, cudaMemcpyDeviceToHost, s);
+  return e == cudaSuccess ? OVRFSR_OK : fail(ctx, OVRFSR_ERR_CUDA, "device->host copy", e);
+}
+
+// ---- stateless dispatches ---------------------------------------------------------------------
+static int check_pair(const ovrfsr_image *src, const ovrfsr_image *dst) {
+  int rc = validate_image(src);
+  if (rc != OVRFSR_OK) return rc;
+  if ((rc = validate_image(dst)) != OVRFSR_OK) return rc;
+  if (dst->format != OVRFSR_FORMAT_RGBA8 && dst->format != OVRFSR_FORMAT_RGBA16F) return OVRFSR_ERR_UNSUPPORTED;
+  return OVRFSR_OK;
+}
+
+int ovrfsr_dispatch_fsr_easu(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[24], int math_mode,
+                             void *stream) {
+  if (!consts) return OVRFSR_ERR_INVALID;
+  int rc = check_pair(src, dst);
+  if (rc != OVRFSR_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = math_mode == OVRFSR_MATH_STRICT ? launch_easu_strict(pass_image(*src), pass_image(*dst), consts, s)
+                                                  : launch_easu_fast(pass_image(*src), pass_image(*dst), consts, s);
+  if (e == cudaErrorInvalidConfiguration || e == cudaErrorInvalidValue) return OVRFSR_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? OVRFSR_OK : OVRFSR_ERR_CUDA;
+}
+
+int ovrfsr_dispatch_fsr_rcas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[12], int math_mode,
+                             void *stream) {
+  if (!consts) return OVRFSR_ERR_INVALID;
+  int rc = check_pair(src, dst);
+  if (rc != OVRFSR_OK) return rc;
+  if (src->width != dst->width || src->height != dst->height) return OVRFSR_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = math_mode == OVRFSR_MATH_STRICT ? launch_rcas_strict(pass_image(*src), pass_image(*dst), consts, s)
+                                                  : launch_rcas_fast(pass_image(*src), pass_image(*dst), consts, s);
+  if (e == cudaErrorInvalidValue) return OVRFSR_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? OVRFSR_OK : OVRFSR_ERR_CUDA;
+}
+
+// ---- host constants -----------------------------------------------------------------------------
+void ovrfsr_output_size(uint32_t in_w, uint32_t in_h, float render_scale, uint32_t *out_w, uint32_t *out_h) {
+  uint32_t w = 0, h = 0;
+  host::output_size(in_w, in_h, render_scale, &w, &h);
+  if (out_w) *out_w = w;
+  if (out_h) *out_h = h;
+}
+void ovrfsr_fsr_easu_con(uint32_t con[16], float vw, float vh, float iw, float ih, float ow, float oh) {
+  host::fsr_easu_con(con, vw, vh, iw, ih, ow, oh);
+}
+void ovrfsr_fsr_rcas_con(uint32_t con[4], float stops) { host::fsr_rcas_con(con, stops); }
+void ovrfsr_make_upscale_constants(uint32_t consts[24], const ovrfsr_config *cfg, int eye, int only_one_eye, uint32_t in_w,
+                                   uint32_t in_h, uint32_t out_w, uint32_t out_h) {
+  host::make_upscale_constants(consts, *cfg, eye, only_one_eye != 0, in_w, in_h, out_w, out_h);
+}
+void ovrfsr_make_sharpen_constants(uint32_t consts[12], const ovrfsr_config *cfg, int eye, int only_one_eye, uint32_t out_w,
+                                   uint32_t out_h) {
+  host::make_sharpen_constants(consts, *cfg, eye, only_one_eye != 0, out_w, out_h);
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+int ovrfsr_get_upscale_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts[24]) {
+  if (!ctx || !consts || (eye != 0 && eye != 1) || !ctx->initialized) return OVRFSR_ERR_INVALID;
+  std::memcpy(consts, ctx->upscaleConstants[ctx->textureContainsOnlyOneEye ? eye : 0], 96);
+  return OVRFSR_OK;
+}
+int ovrfsr_get_sharpen_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts[12]) {
+  if (!ctx || !consts || (eye != 0 && eye != 1) || !ctx->initialized) return OVRFSR_ERR_INVALID;
+  std::memcpy(consts, ctx->sharpenConstants[ctx->textureContainsOnlyOneEye ? eye : 0], 48);
+  return OVRFSR_OK;
+}
+uint64_t ovrfsr_kernel_launches(void) { return ovrfsr::g_launches.load(std::memory_order_relaxed); }
+
+int ovrfsr_get_gpu_time_ms(ovrfsr_ctx *ctx, float *mean_ms) {
+  if (!ctx || !mean_ms) return 0;
+  harvest_queries(ctx);
+  if (ctx->countedQueries == 0) return 0;
+  // "Average GPU processing time for upscale", x2 when each texture holds one eye (PostProcessor.cpp:619-626)
+  float avg = ctx->summedGpuTime / (float)ctx->countedQueries;
+  if (ctx->textureContainsOnlyOneEye) avg *= 2;
+  *mean_ms = avg;
+  return ctx->countedQueries;
+}
+
+const char *ovrfsr_last_error(const ovrfsr_ctx *ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
+
+const char *ovrfsr_status_string(int status) {
+  switch (status) {
+    case OVRFSR_OK: return "ok";
+    case OVRFSR_ERR_INVALID: return "invalid argument";
+    case OVRFSR_ERR_UNSUPPORTED: return "unsupported format or scale";
+    case OVRFSR_ERR_CUDA: return "CUDA failure or no device";
+    case OVRFSR_ERR_NOMEM: return "out of memory";
+    case OVRFSR_PASSTHROUGH: return "post-processing disabled: pass-through";
+    default: return "unknown status";
+  }
+}
+uint32_t ovrfsr_version(void) { return OVRFSR_VERSION; }
+
+int ovrfsr_image_alloc(ovrfsr_image *img, uint32_t width, uint32_t height, int32_t format) {
+  if (!img || width == 0 || height == 0 || !valid_format(format)) return OVRFSR_ERR_INVALID;
+  DeviceImage d;
+  if (!d.alloc(width, height, format)) return OVRFSR_ERR_NOMEM;
+  *img = d.img;
+  return OVRFSR_OK;
+}
+void ovrfsr_image_free(ovrfsr_image *img) {
+  if (img && img->data) cudaFree(img->data);
+  if (img) *img = ovrfsr_image{};
+}
+
+} // extern "C"

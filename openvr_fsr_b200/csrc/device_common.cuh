@@ -1,0 +1,115 @@
+// device_common.cuh -- pixel-format decode/encode and small math helpers shared by the
+// FSR and NIS kernels (sm_100a).  Product code: never includes anything from oracle/.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ovrfsr.h"
+
+namespace ovrfsr {
+
+// The math mode of this translation unit: the same sources are compiled twice,
+//   kernels_fast.cu   : -fmad=true,  kStrict=false  (FMA contraction + regrouped taps)
+//   kernels_strict.cu : -fmad=false, kStrict=true   (reference operation order, bit-exact)
+#ifndef OVRFSR_STRICT
+#error "compile through kernels_fast.cu / kernels_strict.cu"
+#endif
+constexpr bool kStrict = (OVRFSR_STRICT != 0);
+
+struct ImageRO { const uint8_t *ptr; uint32_t pitch; int w, h; };
+struct ImageRW { uint8_t *ptr; uint32_t pitch; int w, h; };
+
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+
+// ffx_a.h:1843-1845 -- integer bit-trick approximations (bit-exact on any IEEE machine)
+__device__ __forceinline__ float prx_lo_rcp(float a) { return u2f(0x7ef07ebbu - f2u(a)); }
+__device__ __forceinline__ float prx_lo_rsq(float a) { return u2f(0x5f347d74u - (f2u(a) >> 1)); }
+__device__ __forceinline__ float prx_med_rcp(float a) {
+  float b = u2f(0x7ef19fffu - f2u(a));
+  return b * (-b * a + 2.0f);
+}
+
+// rcp(): IEEE 1/x in strict mode (what the checker computes), MUFU.RCP (<=1 ulp, D3D's own
+// tolerance for rcp) in fast mode.
+__device__ __forceinline__ float rcp_mode(float a) {
+  if constexpr (kStrict) {
+    return __frcp_rn(a);
+  } else {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+  }
+}
+
+// byte k of a packed texel -> exact float(v): PRMT builds 0x4B0000vv (= 2^23 + v), one FADD removes 2^23.
+template <int K>
+__device__ __forceinline__ float byte_to_float(uint32_t p) {
+  return u2f(__byte_perm(p, 0x4B000000u, 0x7540 | K)) - 8388608.0f;
+}
+// UNORM8 decode = correctly rounded v/255 (D3D11 UNORM->FLOAT).  q=v*r; one FMA residual step makes
+// it exact for all 256 inputs (verified exhaustively in tests/test_host_logic.py) without a divide.
+__device__ __forceinline__ float unorm8(float v) {
+  const float r = 1.0f / 255.0f;
+  float q = __fmul_rn(v, r);
+  float e = __fmaf_rn(-255.0f, q, v);
+  return __fmaf_rn(e, r, q);
+}
+
+// texel fetch -> float4 rgba.  No bounds logic here.
+template <int FMT>
+__device__ __forceinline__ float4 fetch_texel(const uint8_t *__restrict__ row, int x) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGBA16F) {
+    const uint2 p = __ldg(reinterpret_cast<const uint2 *>(row) + x);
+    const __half2 lo = *reinterpret_cast<const __half2 *>(&p.x), hi = *reinterpret_cast<const __half2 *>(&p.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(row) + x);
+    const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p));
+    const float c2 = unorm8(byte_to_float<2>(p)), c3 = unorm8(byte_to_float<3>(p));
+    if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, c3);
+    return make_float4(c0, c1, c2, c3);
+  }
+}
+
+// FLOAT -> UNORM8: (uint)(saturate(v)*255 + 0.5); saturate(NaN) = 0 like D3D.
+__device__ __forceinline__ uint32_t to_unorm8(float v) {
+  float s = __saturatef(v);
+  float t;
+  if constexpr (kStrict) t = __fadd_rn(__fmul_rn(s, 255.0f), 0.5f);
+  else t = __fmaf_rn(s, 255.0f, 0.5f);
+  return (uint32_t)t; // F2I.TRUNC; t is in [0.5, 255.5]
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_texel(uint8_t *__restrict__ row, int x, float r, float g, float b, float a) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGBA16F) {
+    const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+    uint2 p;
+    p.x = *reinterpret_cast<const uint32_t *>(&lo);
+    p.y = *reinterpret_cast<const uint32_t *>(&hi);
+    reinterpret_cast<uint2 *>(row)[x] = p;
+  } else {
+    const uint32_t p = to_unorm8(r) | (to_unorm8(g) << 8) | (to_unorm8(b) << 16) | (to_unorm8(a) << 24);
+    reinterpret_cast<uint32_t *>(row)[x] = p;
+  }
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t pack_rgba8_opaque(float r, float g, float b) {
+  return to_unorm8(r) | (to_unorm8(g) << 8) | (to_unorm8(b) << 16) | 0xff000000u;
+}
+
+// Workgroup radius test (fsr_easu.hlsl:40-44, fsr_rcas.hlsl:31-35, NIS_Upscale.hlsl:98-101):
+// wrapping u32 arithmetic against both eye centres at group granularity.
+__device__ __forceinline__ bool group_inside(uint32_t gcx, uint32_t gcy, const uint32_t centre[4], uint32_t radiusSq) {
+  const uint32_t d1x = centre[0] - gcx, d1y = centre[1] - gcy;
+  const uint32_t d2x = centre[2] - gcx, d2y = centre[3] - gcy;
+  return (d1x * d1x + d1y * d1y) <= radiusSq || (d2x * d2x + d2y * d2y) <= radiusSq;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+} // namespace ovrfsr

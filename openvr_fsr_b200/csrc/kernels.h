@@ -1,0 +1,22 @@
+// kernels.h -- host-visible launchers of the sm_100a kernels, one set per math mode.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ovrfsr.h"
+
+namespace ovrfsr {
+
+struct PassImage { void *ptr; uint32_t pitch; int w, h; int format; };
+
+// FSR (fsr_kernels.cuh).  consts are the reference's constant-buffer layouts.
+cudaError_t launch_easu_fast(const PassImage &src, const PassImage &dst, const uint32_t consts[24], cudaStream_t s);
+cudaError_t launch_easu_strict(const PassImage &src, const PassImage &dst, const uint32_t consts[24], cudaStream_t s);
+cudaError_t launch_rcas_fast(const PassImage &src, const PassImage &dst, const uint32_t consts[12], cudaStream_t s);
+cudaError_t launch_rcas_strict(const PassImage &src, const PassImage &dst, const uint32_t consts[12], cudaStream_t s);
+
+// bumped once per kernel launch by every launcher (ovrfsr_kernel_launches)
+void count_launch();
+
+} // namespace ovrfsr
