@@ -48,6 +48,8 @@ typedef enum ovrfsr_format {
   OVRFSR_FORMAT_RGBA8 = 0,   /* DXGI_FORMAT_R8G8B8A8_UNORM (sRGB variants are viewed as UNORM, :50-61) */
   OVRFSR_FORMAT_BGRA8 = 1,   /* DXGI_FORMAT_B8G8R8A8_UNORM */
   OVRFSR_FORMAT_RGBA16F = 2, /* DXGI_FORMAT_R16G16B16A16_FLOAT */
+  OVRFSR_FORMAT_RGBA32F = 3, /* DXGI_FORMAT_R32G32B32A32_FLOAT (input: PostProcessor.cpp:32-33; as an output it
+                                exposes the pre-quantisation result) */
   OVRFSR_FORMAT_AUTO = -1    /* output only: DetermineOutputFormat(), :63-74 -> RGBA8 */
 } ovrfsr_format;
 

@@ -58,7 +58,9 @@ def _format_of(t) -> int:
         return L.FORMAT_RGBA8
     if t.dtype == torch.float16:
         return L.FORMAT_RGBA16F
-    raise TypeError("eye textures are uint8 (RGBA8/BGRA8) or float16 (RGBA16F) tensors of shape (H, W, 4)")
+    if t.dtype == torch.float32:
+        return L.FORMAT_RGBA32F
+    raise TypeError("eye textures are uint8 (RGBA8/BGRA8), float16 (RGBA16F) or float32 (RGBA32F) tensors (H, W, 4)")
 
 
 def image_of(t, fmt: int | None = None) -> L.Image:
@@ -78,8 +80,11 @@ def output_size(in_w: int, in_h: int, render_scale: float) -> tuple[int, int]:
 
 def _stream_ptr(stream) -> int:
     import torch
-    s = torch.cuda.current_stream() if stream is None else stream
-    return s.cuda_stream
+    if stream is None:
+        if not torch.cuda.is_available():
+            return 0  # the C ABI then reports OVRFSR_ERR_CUDA itself (no device)
+        stream = torch.cuda.current_stream()
+    return stream.cuda_stream
 
 
 class PostProcessor:
@@ -149,8 +154,7 @@ class PostProcessor:
 def _wrap_device(img: L.Image, device):
     """torch view over a ctx-owned device image (no copy)."""
     import torch
-    elem = 2 if img.format == L.FORMAT_RGBA16F else 1
-    dtype = torch.float16 if img.format == L.FORMAT_RGBA16F else torch.uint8
+    elem = {L.FORMAT_RGBA16F: 2, L.FORMAT_RGBA32F: 4}.get(img.format, 1)
     nbytes = img.pitch * img.height
 
     class _Holder:
@@ -159,9 +163,10 @@ def _wrap_device(img: L.Image, device):
     h = _Holder()
     h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (img.data, False), "version": 2}
     flat = torch.as_tensor(h, device=device)
-    rows = flat.view(img.height, img.pitch)[:, : img.width * 4 * elem]
     if elem == 2:
         return torch.as_strided(flat.view(torch.float16), (img.height, img.width, 4), (img.pitch // 2, 4, 1))
+    if elem == 4:
+        return torch.as_strided(flat.view(torch.float32), (img.height, img.width, 4), (img.pitch // 4, 4, 1))
     return torch.as_strided(flat, (img.height, img.width, 4), (img.pitch, 4, 1))
 
 

@@ -22,8 +22,8 @@ namespace {
 
 constexpr int kQueryCount = 6; // QUERY_COUNT, PostProcessor.h:78
 
-inline uint32_t bytes_per_pixel(int fmt) { return fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u; }
-inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGBA16F; }
+inline uint32_t bytes_per_pixel(int fmt) { return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u); }
+inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGBA32F; }
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 struct DeviceImage {
@@ -117,8 +117,8 @@ int prepare_resources(ovrfsr_ctx *c, const ovrfsr_image *src) {
   if (c->outputWidth == 0 || c->outputHeight == 0) return fail(c, OVRFSR_ERR_INVALID, "output size is zero");
   // DetermineOutputFormat (PostProcessor.cpp:63-74): RGBA8 unless the caller asks for the FP16 extension
   c->outFormat = c->cfg.output_format == OVRFSR_FORMAT_AUTO ? OVRFSR_FORMAT_RGBA8 : c->cfg.output_format;
-  if (c->outFormat != OVRFSR_FORMAT_RGBA8 && c->outFormat != OVRFSR_FORMAT_RGBA16F)
-    return fail(c, OVRFSR_ERR_UNSUPPORTED, "output format must be RGBA8 or RGBA16F");
+  if (c->outFormat != OVRFSR_FORMAT_RGBA8 && c->outFormat != OVRFSR_FORMAT_RGBA16F && c->outFormat != OVRFSR_FORMAT_RGBA32F)
+    return fail(c, OVRFSR_ERR_UNSUPPORTED, "output format must be RGBA8, RGBA16F or RGBA32F");
   const bool one = c->textureContainsOnlyOneEye;
   const int neyes = one ? 2 : 1;
   for (int e = 0; e < neyes; ++e) {
@@ -357,7 +357,7 @@ static int check_pair(const ovrfsr_image *src, const ovrfsr_image *dst) {
   int rc = validate_image(src);
   if (rc != OVRFSR_OK) return rc;
   if ((rc = validate_image(dst)) != OVRFSR_OK) return rc;
-  if (dst->format != OVRFSR_FORMAT_RGBA8 && dst->format != OVRFSR_FORMAT_RGBA16F) return OVRFSR_ERR_UNSUPPORTED;
+  if (dst->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED; /* outputs are RGBA8 (reference) or float */
   return OVRFSR_OK;
 }
 

@@ -8,14 +8,24 @@
 
 #include "../../include/ovrfsr.h"
 
-namespace ovrfsr {
-
 // The math mode of this translation unit: the same sources are compiled twice,
 //   kernels_fast.cu   : -fmad=true,  kStrict=false  (FMA contraction + regrouped taps)
 //   kernels_strict.cu : -fmad=false, kStrict=true   (reference operation order, bit-exact)
+// Every device symbol lives in a mode-specific inline namespace so that the two builds of the same
+// template (e.g. easu_kernel<0,0>) get DIFFERENT mangled names; without it the linker folds the two
+// weak instantiations into one and both launchers start the same kernel.
 #ifndef OVRFSR_STRICT
 #error "compile through kernels_fast.cu / kernels_strict.cu"
 #endif
+#if OVRFSR_STRICT
+#define OVRFSR_MODE_NS strict_math
+#else
+#define OVRFSR_MODE_NS fast_math
+#endif
+
+namespace ovrfsr {
+inline namespace OVRFSR_MODE_NS {
+
 constexpr bool kStrict = (OVRFSR_STRICT != 0);
 
 struct ImageRO { const uint8_t *ptr; uint32_t pitch; int w, h; };
@@ -61,7 +71,9 @@ __device__ __forceinline__ float unorm8(float v) {
 // texel fetch -> float4 rgba.  No bounds logic here.
 template <int FMT>
 __device__ __forceinline__ float4 fetch_texel(const uint8_t *__restrict__ row, int x) {
-  if constexpr (FMT == OVRFSR_FORMAT_RGBA16F) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGBA32F) {
+    return __ldg(reinterpret_cast<const float4 *>(row) + x);
+  } else if constexpr (FMT == OVRFSR_FORMAT_RGBA16F) {
     const uint2 p = __ldg(reinterpret_cast<const uint2 *>(row) + x);
     const __half2 lo = *reinterpret_cast<const __half2 *>(&p.x), hi = *reinterpret_cast<const __half2 *>(&p.y);
     const float2 a = __half22float2(lo), b = __half22float2(hi);
@@ -86,7 +98,9 @@ __device__ __forceinline__ uint32_t to_unorm8(float v) {
 
 template <int FMT>
 __device__ __forceinline__ void store_texel(uint8_t *__restrict__ row, int x, float r, float g, float b, float a) {
-  if constexpr (FMT == OVRFSR_FORMAT_RGBA16F) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGBA32F) {
+    reinterpret_cast<float4 *>(row)[x] = make_float4(r, g, b, a);
+  } else if constexpr (FMT == OVRFSR_FORMAT_RGBA16F) {
     const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
     uint2 p;
     p.x = *reinterpret_cast<const uint32_t *>(&lo);
@@ -112,4 +126,10 @@ __device__ __forceinline__ bool group_inside(uint32_t gcx, uint32_t gcy, const u
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// D3D11 samplers convert the scaled texture coordinate to fixed point with 8 fractional bits
+// (D3D11_SUBTEXEL_FRACTIONAL_BIT_COUNT): snap to 1/256 texel, round to nearest.  x256 is exact, so this is
+// contraction-proof.
+__device__ __forceinline__ float snap_subtexel(float s) { return floorf(fmaf(s, 256.0f, 0.5f)) * (1.0f / 256.0f); }
+
+} // inline namespace OVRFSR_MODE_NS
 } // namespace ovrfsr

@@ -20,6 +20,7 @@
 #include "device_common.cuh"
 
 namespace ovrfsr {
+inline namespace OVRFSR_MODE_NS {
 
 constexpr int kTileW = 64;   // output tile of one CTA
 constexpr int kTileH = 32;
@@ -195,7 +196,7 @@ __device__ __forceinline__ float3 easu_filter(const float4 *__restrict__ sC, con
 }
 
 // Bilinear(), fsr_easu.hlsl:33-36: SampleLevel(linearClamp, float2(pos)/Radius.zw) -- no half-texel
-// offset.  Reads the same clamped colour tile.
+// offset; coordinates snapped to 1/256 texel like D3D11's fixed-point sampler.  Reads the same clamped colour tile.
 __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, int tw, int th, int sx0, int sy0, int x,
                                                 int y, const EasuArgs &a) {
   const float u = (float)x / a.radW, v = (float)y / a.radH;
@@ -207,6 +208,8 @@ __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, i
     sx = fmaf(u, (float)a.src.w, -0.5f);
     sy = fmaf(v, (float)a.src.h, -0.5f);
   }
+  sx = snap_subtexel(sx);
+  sy = snap_subtexel(sy);
   const float fx0 = floorf(sx), fy0 = floorf(sy);
   const float fx = sx - fx0, fy = sy - fy0;
   const int tx0 = clampi((int)fx0 - sx0, 0, tw - 1), tx1 = clampi((int)fx0 + 1 - sx0, 0, tw - 1);
@@ -357,4 +360,5 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const RcasArgs a) {
   }
 }
 
+} // inline namespace OVRFSR_MODE_NS
 } // namespace ovrfsr

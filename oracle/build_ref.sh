@@ -10,7 +10,7 @@
 # What is compiled (reference @ 2146b45):
 #   consts_ref.cpp : ffx_a.h + ffx_fsr1.h + NIS_Config.h under A_CPU, as shipped
 #   fsr_ref.cpp    : ffx_fsr1.h:239-437 (EASU), :684-769 (RCAS), ffx_a.h:1843-1845, behind an HLSL type shim
-#   nis_ref.cpp    : NIS_Scaler.h verbatim (twice: NIS_SCALER=1 and 0) behind an HLSL type shim
+#   nis_ref_{scaler,sharpen}.cpp : NIS_Scaler.h verbatim (NIS_SCALER=1 / 0) behind an HLSL type shim
 # The reference's own build system (Visual Studio + fxc, src/CMakeLists.txt:155-170) is not run.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -38,9 +38,13 @@ HLSL2CPP='s/\b(inout|out) (A[A-Z]+[0-9])\b/\2\&/g'
 sed -n '239,437p' "$FSR1" | sed -E "$HLSL2CPP" > "$TMP/easu_lines.inc"
 sed -n '684,769p' "$FSR1" | sed -E "$HLSL2CPP" > "$TMP/rcas_lines.inc"
 sed -n '1843,1845p' "$FFXA" > "$TMP/ffx_prx.inc"
+# NIS_Scaler.h verbatim except the HLSL float literal of NIS_SCALE_FLOAT (unsuffixed = double in C++)
+NIS="$REF/src/nis/NIS_Scaler.h"
+grep -q '^#define NIS_SCALE_FLOAT 255.0$' "$NIS" || { echo "NIS_SCALE_FLOAT anchor moved"; exit 1; }
+sed 's/^#define NIS_SCALE_FLOAT 255.0$/#define NIS_SCALE_FLOAT 255.0f/' "$NIS" > "$TMP/NIS_Scaler_cpp.h"
 
 OBJS=()
-for f in consts_ref fsr_ref nis_ref; do
+for f in consts_ref fsr_ref nis_ref_scaler nis_ref_sharpen; do
   [ -f "$HERE/ref_shim/$f.cpp" ] || continue
   $CXX $CXXFLAGS -I"$REF/src" -I"$TMP" -c "$HERE/ref_shim/$f.cpp" -o "$TMP/$f.o"
   OBJS+=("$TMP/$f.o")

@@ -9,7 +9,7 @@
  *   Gather{Red,Green,Blue} 2x2 footprint, clamp to edge, order
  *                          .w .z / .x .y                        (fsr_easu.hlsl:21-23,
  *                                                                ffx_fsr1.h:333-343)
- *   SampleLevel(linear clamp) bilinear, float weights           (fsr_easu.hlsl:34,
+ *   SampleLevel(linear clamp) bilinear, 8-bit sub-texel weights (fsr_easu.hlsl:34,
  *                                                                NIS_Upscale.hlsl:87)
  *   RWTexture2D store     float4 -> UNORM8 / FP16, bounds-checked (PostProcessor.cpp:340-358)
  */
@@ -61,12 +61,14 @@ static inline uint16_t ovo_float_to_half(float f) {
   return (uint16_t)(s | r);
 }
 
-static inline int ovo_bpp(int format) { return format == OVO_FMT_RGBA16F ? 8 : 4; }
+static inline int ovo_bpp(int format) { return format == OVO_FMT_RGBA32F ? 16 : (format == OVO_FMT_RGBA16F ? 8 : 4); }
 
 /* in-bounds texel fetch -> float4 (rgba) */
 static inline void ovo_texel(const ovo_image *im, int x, int y, float o[4]) {
   const uint8_t *row = (const uint8_t *)im->data + (size_t)y * (size_t)im->pitch;
-  if (im->format == OVO_FMT_RGBA16F) {
+  if (im->format == OVO_FMT_RGBA32F) {
+    memcpy(o, row + (size_t)x * 16, 16);
+  } else if (im->format == OVO_FMT_RGBA16F) {
     const uint16_t *p = (const uint16_t *)(row + (size_t)x * 8);
     o[0] = ovo_half_to_float(p[0]); o[1] = ovo_half_to_float(p[1]);
     o[2] = ovo_half_to_float(p[2]); o[3] = ovo_half_to_float(p[3]);
@@ -92,9 +94,14 @@ static inline void ovo_texel_clamp(const ovo_image *im, int x, int y, float o[4]
   ovo_texel(im, x, y, o);
 }
 
-/* SampleLevel(linearClamp, uv, 0): bilinear at normalised uv, float weights */
+/* SampleLevel(linearClamp, uv, 0): bilinear at normalised uv.  D3D11 converts the scaled texture
+ * coordinate to fixed point with 8 fractional bits before filtering (functional spec 7.18.8 /
+ * D3D11_SUBTEXEL_FRACTIONAL_BIT_COUNT = 8), which every D3D11 GPU implements: the coordinate is snapped
+ * to 1/256 texel (round to nearest), so weights are multiples of 1/256 and a sample aimed at a texel
+ * centre returns exactly that texel (NVScaler relies on this for its luma taps, NIS_Scaler.h:642-651). */
+static inline float ovo_snap_subtexel(float s) { return floorf(s * 256.0f + 0.5f) * (1.0f / 256.0f); }
 static inline void ovo_sample_linear(const ovo_image *im, float u, float v, float o[4]) {
-  float sx = u * (float)im->width - 0.5f, sy = v * (float)im->height - 0.5f;
+  float sx = ovo_snap_subtexel(u * (float)im->width - 0.5f), sy = ovo_snap_subtexel(v * (float)im->height - 0.5f);
   float fx0 = floorf(sx), fy0 = floorf(sy);
   float fx = sx - fx0, fy = sy - fy0;
   int x0 = (int)fx0, y0 = (int)fy0;
@@ -115,7 +122,9 @@ static inline void ovo_sample_linear(const ovo_image *im, float u, float v, floa
 static inline void ovo_store(const ovo_image *im, int x, int y, const float c[4]) {
   if (x < 0 || y < 0 || x >= im->width || y >= im->height) return;
   uint8_t *row = (uint8_t *)im->data + (size_t)y * (size_t)im->pitch;
-  if (im->format == OVO_FMT_RGBA16F) {
+  if (im->format == OVO_FMT_RGBA32F) {
+    memcpy(row + (size_t)x * 16, c, 16);
+  } else if (im->format == OVO_FMT_RGBA16F) {
     uint16_t *p = (uint16_t *)(row + (size_t)x * 8);
     for (int i = 0; i < 4; ++i) p[i] = ovo_float_to_half(c[i]);
   } else {

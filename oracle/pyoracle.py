@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-FMT_RGBA8, FMT_BGRA8, FMT_RGBA16F = 0, 1, 2
+FMT_RGBA8, FMT_BGRA8, FMT_RGBA16F, FMT_RGBA32F = 0, 1, 2, 3
 
 
 class Image(C.Structure):
@@ -142,12 +142,12 @@ def ref_lib():
 def _np_format(arr: np.ndarray, fmt: int | None) -> int:
     if fmt is not None:
         return fmt
-    return FMT_RGBA16F if arr.dtype == np.float16 else FMT_RGBA8
+    return {np.dtype(np.float16): FMT_RGBA16F, np.dtype(np.float32): FMT_RGBA32F}.get(arr.dtype, FMT_RGBA8)
 
 
 def as_image(arr: np.ndarray, fmt: int | None = None) -> Image:
-    """arr: (H, W, 4) uint8 or float16, C-contiguous rows (row pitch = arr.strides[0])."""
-    assert arr.ndim == 3 and arr.shape[2] == 4 and arr.dtype in (np.uint8, np.float16)
+    """arr: (H, W, 4) uint8, float16 or float32, C-contiguous rows (row pitch = arr.strides[0])."""
+    assert arr.ndim == 3 and arr.shape[2] == 4 and arr.dtype in (np.uint8, np.float16, np.float32)
     assert arr.strides[2] == arr.itemsize and arr.strides[1] == 4 * arr.itemsize
     return Image(arr.ctypes.data, arr.shape[1], arr.shape[0], arr.strides[0], _np_format(arr, fmt))
 
