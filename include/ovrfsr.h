@@ -55,8 +55,12 @@ typedef enum ovrfsr_format {
 
 /* arithmetic mode of the kernels */
 typedef enum ovrfsr_math {
-  OVRFSR_MATH_FAST = 0,  /* FMA contraction + algebraically regrouped taps; <=1 LSB (RGBA8) vs the reference lines */
-  OVRFSR_MATH_STRICT = 1 /* the reference's operation order, no contraction: bit-identical to the reference lines */
+  OVRFSR_MATH_FAST = 0,  /* FMA contraction + regrouped taps: each pass is <= 1 LSB (RGBA8) from the reference lines
+                            on identical inputs.  Note that EASU -> RGBA8 -> RCAS amplifies a 1-LSB intermediate
+                            difference in dark regions (RCAS divides by the ring maximum), as it does between any two
+                            D3D11 GPUs; use STRICT when the composed result must match to the bit. */
+  OVRFSR_MATH_STRICT = 1 /* the reference's operation order, no contraction: bit-identical to the reference lines,
+                            end to end.  The default of ovrfsr_config_default. */
 } ovrfsr_math;
 
 /* Device-resident image: the CUDA analogue of the ID3D11Texture2D* that Texture_t::handle

@@ -27,7 +27,7 @@ class Config:
     projCentre: tuple = (0.5, 0.5, 0.5, 0.5)
     device: int = -1
     outputFormat: int = L.FORMAT_AUTO
-    mathMode: int = L.MATH_FAST
+    mathMode: int = L.MATH_STRICT
 
     def to_c(self) -> L.Config:
         c = L.Config()

@@ -240,7 +240,7 @@ void ovrfsr_config_default(ovrfsr_config *cfg) {
   cfg->proj_centre[0] = cfg->proj_centre[1] = cfg->proj_centre[2] = cfg->proj_centre[3] = 0.5f;
   cfg->device = -1;
   cfg->output_format = OVRFSR_FORMAT_AUTO;
-  cfg->math_mode = OVRFSR_MATH_FAST;
+  cfg->math_mode = OVRFSR_MATH_STRICT; // parity first: bit-identical to the reference lines end to end
 }
 
 int ovrfsr_create(ovrfsr_ctx **out, const ovrfsr_config *cfg) {

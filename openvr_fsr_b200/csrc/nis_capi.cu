@@ -36,14 +36,49 @@ const float *ovrfsr_nis_coef_usm(void) { std::call_once(g_coefOnce, expand_coef)
 
 } // extern "C"
 
-// NVScaler / NVSharpen dispatches live in nis_kernels.cuh (added with the NIS kernels).
-#ifndef OVRFSR_HAVE_NIS_KERNELS
+// ---- dispatches (ApplyUpscaling / ApplySharpening with useNis, PostProcessor.cpp:385-401,483-496) ------------
+namespace {
+inline uint32_t bpp(int fmt) { return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u); }
+int check(const ovrfsr_image *im, bool isDst) {
+  if (!im || !im->data || im->width == 0 || im->height == 0) return OVRFSR_ERR_INVALID;
+  if (im->format < OVRFSR_FORMAT_RGBA8 || im->format > OVRFSR_FORMAT_RGBA32F) return OVRFSR_ERR_UNSUPPORTED;
+  if (isDst && im->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED;
+  if (im->pitch < im->width * bpp(im->format) || im->pitch % bpp(im->format) ||
+      reinterpret_cast<uintptr_t>(im->data) % bpp(im->format)) return OVRFSR_ERR_INVALID;
+  return OVRFSR_OK;
+}
+PassImage pass(const ovrfsr_image &im) { return PassImage{im.data, im.pitch, (int)im.width, (int)im.height, im.format}; }
+int status_of(cudaError_t e) {
+  if (e == cudaSuccess) return OVRFSR_OK;
+  return (e == cudaErrorInvalidConfiguration || e == cudaErrorInvalidValue) ? OVRFSR_ERR_UNSUPPORTED : OVRFSR_ERR_CUDA;
+}
+} // namespace
+
 extern "C" {
-int ovrfsr_dispatch_nis_scaler(const ovrfsr_image *, const ovrfsr_image *, const void *, int, void *) {
-  return OVRFSR_ERR_UNSUPPORTED;
+
+int ovrfsr_dispatch_nis_scaler(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256, int math_mode,
+                               void *stream) {
+  if (!cfg256) return OVRFSR_ERR_INVALID;
+  int rc = check(src, false);
+  if (rc != OVRFSR_OK || (rc = check(dst, true)) != OVRFSR_OK) return rc;
+  const float *coef = ovrfsr_nis_coef_scale(); // g_coefScale and g_coefUsm are contiguous? no: upload buffer below
+  static float both[2][64 * 8];
+  static std::once_flag once;
+  std::call_once(once, [&] { std::memcpy(both[0], coef, sizeof(both[0])); std::memcpy(both[1], ovrfsr_nis_coef_usm(), sizeof(both[1])); });
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return status_of(math_mode == OVRFSR_MATH_STRICT ? launch_nis_scaler_strict(pass(*src), pass(*dst), cfg256, &both[0][0], s)
+                                                   : launch_nis_scaler_fast(pass(*src), pass(*dst), cfg256, &both[0][0], s));
 }
-int ovrfsr_dispatch_nis_sharpen(const ovrfsr_image *, const ovrfsr_image *, const void *, int, void *) {
-  return OVRFSR_ERR_UNSUPPORTED;
+
+int ovrfsr_dispatch_nis_sharpen(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256, int math_mode,
+                                void *stream) {
+  if (!cfg256) return OVRFSR_ERR_INVALID;
+  int rc = check(src, false);
+  if (rc != OVRFSR_OK || (rc = check(dst, true)) != OVRFSR_OK) return rc;
+  if (src->width != dst->width || src->height != dst->height) return OVRFSR_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return status_of(math_mode == OVRFSR_MATH_STRICT ? launch_nis_sharpen_strict(pass(*src), pass(*dst), cfg256, nullptr, s)
+                                                   : launch_nis_sharpen_fast(pass(*src), pass(*dst), cfg256, nullptr, s));
 }
-}
-#endif
+
+} // extern "C"

@@ -66,3 +66,45 @@ def test_easu_rcas_vs_oracle(cuda, iw, ih, scale, radius):
 def test_smoke_entry(cuda):
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_full_frame_c2_strict_bit_exact_and_fast_statistics(cuda):
+    """BASELINE.json configs[1] at full size (1683x1869 -> 2244x2492), one eye, reference default radius 0.5 and
+    mask-off radius 2.0: strict is bit-identical end to end; fast is <= 1 LSB per pass on identical inputs, and its
+    composed EASU->RCAS deviation is reported (RCAS amplifies 1-LSB intermediates in dark regions)."""
+    import os
+    import torch
+    import openvr_fsr_b200 as ovr
+    from openvr_fsr_b200 import synth
+    from oracle import pyoracle as po
+    iw, ih, scale = 1683, 1869, 0.75
+    ow, oh = po.output_size(iw, ih, scale)
+    src = synth.natural_rgba8(iw, ih, 1)
+    t = torch.from_numpy(src).to(cuda)
+    nt = os.cpu_count() or 1
+    for radius in (0.5, 2.0):
+        uc = po.upscale_constants(0, True, iw, ih, ow, oh, radius=radius)
+        sc = po.sharpen_constants(0, True, ow, oh, radius=radius, sharpness=0.9)
+        easu = po.easu(src, ow, oh, uc, nthreads=nt)
+        want = po.rcas(easu, sc, nthreads=nt)
+        pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=scale, sharpness=0.9, radius=radius,
+                                          mathMode=ovr.MATH_STRICT))
+        got = pp.apply(0, t).cpu().numpy()
+        pp.close()
+        assert np.array_equal(got, want)
+        f_easu = torch.empty((oh, ow, 4), dtype=torch.uint8, device=cuda)
+        f_rcas = torch.empty_like(f_easu)
+        ovr.fsr_easu(t, f_easu, uc.words(), ovr.MATH_FAST)
+        ovr.fsr_rcas(torch.from_numpy(easu).to(cuda), f_rcas, sc.words(), ovr.MATH_FAST)
+        torch.cuda.synchronize()
+        de = np.abs(f_easu.cpu().numpy().astype(np.int16) - easu.astype(np.int16))
+        dr = np.abs(f_rcas.cpu().numpy().astype(np.int16) - want.astype(np.int16))
+        assert de.max() <= 1 and dr.max() <= 1
+        assert (de > 0).mean() < 2e-3 and (dr > 0).mean() < 2e-3  # and rare
+        pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=scale, sharpness=0.9, radius=radius,
+                                          mathMode=ovr.MATH_FAST))
+        comp = np.abs(pp.apply(0, t).cpu().numpy().astype(np.int16) - want.astype(np.int16))
+        pp.close()
+        print(f"radius {radius}: fast per-pass mismatch EASU {(de > 0).mean():.2e} RCAS {(dr > 0).mean():.2e}; "
+              f"composed: {(comp > 1).mean():.2e} of channel values beyond 1 LSB, max {comp.max()}")
+        assert (comp > 1).mean() < 1e-3
