@@ -126,6 +126,12 @@ __device__ __forceinline__ bool group_inside(uint32_t gcx, uint32_t gcy, const u
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// Coordinate arithmetic is NEVER contracted, in either math mode: its result feeds floor()/int conversion, and a
+// value that lands exactly on an integer (e.g. out x=140 of a 211->281 upscale maps to source 105.0) would pick a
+// different texel footprint -- and a different de-ring clamp set -- if a*b+c were fused.  The reference leaves this
+// to the shader compiler; the checker defines it as separate IEEE mul and add.
+__device__ __forceinline__ float mul_add_unfused(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+
 // D3D11 samplers convert the scaled texture coordinate to fixed point with 8 fractional bits
 // (D3D11_SUBTEXEL_FRACTIONAL_BIT_COUNT): snap to 1/256 texel, round to nearest.  x256 is exact, so this is
 // contraction-proof.

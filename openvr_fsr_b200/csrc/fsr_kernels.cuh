@@ -47,10 +47,7 @@ struct RcasArgs {
 
 // out pixel -> source position; the same instruction sequence is used for the tile origin and
 // for every pixel so that both agree to the bit.
-__device__ __forceinline__ float easu_pos(int p, float scale, float offs) {
-  if constexpr (kStrict) return __fadd_rn(__fmul_rn((float)p, scale), offs);
-  else return __fmaf_rn((float)p, scale, offs);
-}
+__device__ __forceinline__ float easu_pos(int p, float scale, float offs) { return mul_add_unfused((float)p, scale, offs); }
 
 // FsrEasuSetF (ffx_fsr1.h:275-313) minus the bilinear weight: the per-source-texel part.
 //   a
@@ -200,16 +197,8 @@ __device__ __forceinline__ float3 easu_filter(const float4 *__restrict__ sC, con
 __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, int tw, int th, int sx0, int sy0, int x,
                                                 int y, const EasuArgs &a) {
   const float u = (float)x / a.radW, v = (float)y / a.radH;
-  float sx, sy;
-  if constexpr (kStrict) {
-    sx = __fadd_rn(__fmul_rn(u, (float)a.src.w), -0.5f);
-    sy = __fadd_rn(__fmul_rn(v, (float)a.src.h), -0.5f);
-  } else {
-    sx = fmaf(u, (float)a.src.w, -0.5f);
-    sy = fmaf(v, (float)a.src.h, -0.5f);
-  }
-  sx = snap_subtexel(sx);
-  sy = snap_subtexel(sy);
+  const float sx = snap_subtexel(mul_add_unfused(u, (float)a.src.w, -0.5f));
+  const float sy = snap_subtexel(mul_add_unfused(v, (float)a.src.h, -0.5f));
   const float fx0 = floorf(sx), fy0 = floorf(sy);
   const float fx = sx - fx0, fy = sy - fy0;
   const int tx0 = clampi((int)fx0 - sx0, 0, tw - 1), tx1 = clampi((int)fx0 + 1 - sx0, 0, tw - 1);
