@@ -49,7 +49,7 @@ __device__ __forceinline__ float rcp_mode(float a) {
     return __frcp_rn(a);
   } else {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); // one MUFU.RCP; operands here are never subnormal
     return r;
   }
 }
@@ -125,6 +125,14 @@ __device__ __forceinline__ bool group_inside(uint32_t gcx, uint32_t gcy, const u
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// Packed FP32x2 (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot for two FP32 lanes.  A scalar operand is
+// broadcast for free (SASS `Rn.F32`), so `bc(w)` costs nothing.
+typedef float2 f2;
+__device__ __forceinline__ f2 bc(float x) { return make_float2(x, x); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
 
 // Coordinate arithmetic is NEVER contracted, in either math mode: its result feeds floor()/int conversion, and a
 // value that lands exactly on an integer (e.g. out x=140 of a 211->281 upscale maps to source 105.0) would pick a

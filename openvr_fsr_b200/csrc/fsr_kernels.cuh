@@ -18,6 +18,7 @@
 #pragma once
 
 #include "device_common.cuh"
+#include "tma_utils.cuh"
 
 namespace ovrfsr {
 inline namespace OVRFSR_MODE_NS {
@@ -192,6 +193,109 @@ __device__ __forceinline__ float3 easu_filter(const float4 *__restrict__ sC, con
   return make_float3(fminf(mxR, fmaxf(mnR, aR * r)), fminf(mxG, fmaxf(mnG, aG * r)), fminf(mxB, fmaxf(mnB, aB * r)));
 }
 
+// ---- fast math: FsrEasuF regrouped for the FP32x2 pipe ----------------------------------------------------
+// Same function as easu_filter, evaluated differently (results differ from the reference lines in the last
+// bits only; <= 1 LSB after RGBA8 rounding):
+//   * the squared rotated/stretched tap distance is a quadratic form of the integer tap offset,
+//       d2(ox,oy) = Q00*dx^2 + 2*Q01*dx*dy + Q11*dy^2,  dx = ox-ppx, dy = oy-ppy,  Q = M^T M,
+//     so one FADD2 + one FFMA2 yield d2 for two horizontally adjacent taps (A_P + B_j, E_P*dy_j);
+//   * the window polynomial is expanded: 25/16*(2/5 t-1)^2 - 9/16 = (t/4 - 5/4) t + 1;
+//   * the colour tile stores (r,g,b,1): two FFMA2 per tap accumulate (r,g) and (b, weight) at once;
+//   * feature blending, normalisation and setup are packed the same way.  ~100 packed + ~40 scalar FP
+//     instructions per pixel instead of ~250 scalar ones.
+__device__ __forceinline__ f2 easu_w2(f2 A, float B, f2 E, float dy, float clp, float lob) {
+  f2 t = fma2(E, bc(dy), add2(A, bc(B)));
+  t.x = fminf(t.x, clp);
+  t.y = fminf(t.y, clp);
+  const f2 base = fma2(fma2(t, bc(0.25f), bc(-1.25f)), t, bc(1.0f));
+  f2 win = fma2(t, bc(lob), bc(-1.0f));
+  win = mul2(win, win);
+  return mul2(base, win);
+}
+__device__ __forceinline__ void easu_acc(f2 &aRG, f2 &aBW, const float4 c, float w) {
+  aRG = fma2(make_float2(c.x, c.y), bc(w), aRG);
+  aBW = fma2(make_float2(c.z, c.w), bc(w), aBW); // c.w == 1: the weight sum rides along
+}
+
+template <int TW>
+__device__ __forceinline__ float3 easu_filter_fast(const float4 *__restrict__ sC, const float4 *__restrict__ sF, int ix,
+                                                   int iy, float ppx, float ppy) {
+  const float4 *fr = sF + iy * TW + ix;
+  const float4 Ff = fr[0], Fg = fr[1], Fj = fr[TW], Fk = fr[TW + 1];
+  const float qx = 1.0f - ppx, qy = 1.0f - ppy;
+  const f2 wt = mul2(make_float2(qx, ppx), bc(qy)), wb = mul2(make_float2(qx, ppx), bc(ppy)); // (wf,wg) (wj,wk)
+  f2 dir = mul2(make_float2(Ff.x, Ff.y), bc(wt.x));
+  f2 ln = mul2(make_float2(Ff.z, Ff.w), bc(wt.x));
+  dir = fma2(make_float2(Fg.x, Fg.y), bc(wt.y), dir); ln = fma2(make_float2(Fg.z, Fg.w), bc(wt.y), ln);
+  dir = fma2(make_float2(Fj.x, Fj.y), bc(wb.x), dir); ln = fma2(make_float2(Fj.z, Fj.w), bc(wb.x), ln);
+  dir = fma2(make_float2(Fk.x, Fk.y), bc(wb.y), dir); ln = fma2(make_float2(Fk.z, Fk.w), bc(wb.y), ln);
+  float len = ln.x + ln.y;
+
+  f2 dd = mul2(dir, dir);
+  float dirR = dd.x + dd.y;
+  const bool zro = dirR < (float)(1.0 / 32768.0);
+  dirR = zro ? 1.0f : prx_lo_rsq(dirR);
+  dir.x = zro ? 1.0f : dir.x;
+  dir = mul2(dir, bc(dirR));
+  len = len * 0.5f;
+  len *= len;
+  dd = mul2(dir, dir);
+  const float stretch = (dd.x + dd.y) * prx_lo_rcp(fmaxf(fabsf(dir.x), fabsf(dir.y)));
+  const float len0 = fmaf(stretch - 1.0f, len, 1.0f);
+  const float len1 = fmaf(-0.5f, len, 1.0f);
+  const float lob = fmaf((float)((1.0 / 4.0 - 0.04) - 0.5), len, 0.5f);
+  const float clp = prx_lo_rcp(lob);
+
+  // Q = M^T M with M = diag(len0,len1) * Rot(dir):  Q00 = dx^2 L0 + dy^2 L1, Q11 = dy^2 L0 + dx^2 L1, Q01 = dx dy (L0-L1)
+  const float L0 = len0 * len0, L1 = len1 * len1;
+  const float Q00 = fmaf(dd.x, L0, dd.y * L1), Q11 = fmaf(dd.y, L0, dd.x * L1);
+  const float Q01x2 = 2.0f * (dir.x * dir.y) * (L0 - L1);
+  // tap offsets: x pairs (-1,0) (0,1) (1,2), y scalars -1,0,1,2
+  const f2 mpx = bc(-ppx), mpy = bc(-ppy);
+  const f2 dxA = add2(make_float2(-1.0f, 0.0f), mpx), dxB = add2(make_float2(0.0f, 1.0f), mpx),
+           dxC = add2(make_float2(1.0f, 2.0f), mpx);
+  const f2 dyA = add2(make_float2(-1.0f, 0.0f), mpy), dyB = add2(make_float2(1.0f, 2.0f), mpy);
+  const f2 qq = bc(Q00), ee = bc(Q01x2), q11 = bc(Q11);
+  const f2 AA = mul2(mul2(dxA, dxA), qq), AB = mul2(mul2(dxB, dxB), qq), AC = mul2(mul2(dxC, dxC), qq);
+  const f2 EA = mul2(dxA, ee), EB = mul2(dxB, ee), EC = mul2(dxC, ee);
+  const f2 BA = mul2(mul2(dyA, dyA), q11), BB = mul2(mul2(dyB, dyB), q11); // (B_-1,B_0) (B_1,B_2)
+
+  //    b c
+  //  e f g h
+  //  i j k l
+  //    n o
+  const float4 *r0 = sC + (iy - 1) * TW + ix;
+  f2 aRG = bc(0.0f), aBW = bc(0.0f);
+  {
+    const float4 b = r0[0], c = r0[1];
+    const f2 w = easu_w2(AB, BA.x, EB, dyA.x, clp, lob);
+    easu_acc(aRG, aBW, b, w.x); easu_acc(aRG, aBW, c, w.y);
+  }
+  const float4 f = r0[TW], g = r0[TW + 1], j = r0[2 * TW], k = r0[2 * TW + 1];
+  {
+    const float4 e = r0[TW - 1], h = r0[TW + 2];
+    const f2 w0 = easu_w2(AA, BA.y, EA, dyA.y, clp, lob), w1 = easu_w2(AC, BA.y, EC, dyA.y, clp, lob);
+    easu_acc(aRG, aBW, e, w0.x); easu_acc(aRG, aBW, f, w0.y);
+    easu_acc(aRG, aBW, g, w1.x); easu_acc(aRG, aBW, h, w1.y);
+  }
+  {
+    const float4 i = r0[2 * TW - 1], l = r0[2 * TW + 2];
+    const f2 w0 = easu_w2(AA, BB.x, EA, dyB.x, clp, lob), w1 = easu_w2(AC, BB.x, EC, dyB.x, clp, lob);
+    easu_acc(aRG, aBW, i, w0.x); easu_acc(aRG, aBW, j, w0.y);
+    easu_acc(aRG, aBW, k, w1.x); easu_acc(aRG, aBW, l, w1.y);
+  }
+  {
+    const float4 n = r0[3 * TW], o = r0[3 * TW + 1];
+    const f2 w = easu_w2(AB, BB.y, EB, dyB.y, clp, lob);
+    easu_acc(aRG, aBW, n, w.x); easu_acc(aRG, aBW, o, w.y);
+  }
+  const float mnR = fminf(fminf(f.x, fminf(g.x, j.x)), k.x), mxR = fmaxf(fmaxf(f.x, fmaxf(g.x, j.x)), k.x);
+  const float mnG = fminf(fminf(f.y, fminf(g.y, j.y)), k.y), mxG = fmaxf(fmaxf(f.y, fmaxf(g.y, j.y)), k.y);
+  const float mnB = fminf(fminf(f.z, fminf(g.z, j.z)), k.z), mxB = fmaxf(fmaxf(f.z, fmaxf(g.z, j.z)), k.z);
+  const float r = rcp_mode(aBW.y);
+  return make_float3(fminf(mxR, fmaxf(mnR, aRG.x * r)), fminf(mxG, fmaxf(mnG, aRG.y * r)), fminf(mxB, fmaxf(mnB, aBW.x * r)));
+}
+
 // Bilinear(), fsr_easu.hlsl:33-36: SampleLevel(linearClamp, float2(pos)/Radius.zw) -- no half-texel
 // offset; coordinates snapped to 1/256 texel like D3D11's fixed-point sampler.  Reads the same clamped colour tile.
 __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, int tw, int th, int sx0, int sy0, int x,
@@ -212,35 +316,79 @@ __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, i
   return make_float3(tR * wy0 + bR * fy, tG * wy0 + bG * fy, tB * wy0 + bB * fy);
 }
 
-template <int FIN, int FOUT>
-__global__ void __launch_bounds__(kThreads, 2) easu_kernel(const EasuArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int tw = a.tileW, th = a.tileH, tn = tw * th;
-  float4 *sC = reinterpret_cast<float4 *>(smem_raw); // decoded colour, w = luma*2
-  float4 *sF = sC + tn;                              // (dirX, dirY, lenX, lenY) per texel
-  float *sL = reinterpret_cast<float *>(sF + tn);    // luma*2 plane (conflict-free stencil reads)
+// 3-channel decode of a packed RGBA8/BGRA8 texel (EASU never reads source alpha: its output alpha is 1)
+template <int FMT>
+__device__ __forceinline__ float4 decode_rgb1(uint32_t p) {
+  const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p)), c2 = unorm8(byte_to_float<2>(p));
+  if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, 1.0f);
+  return make_float4(c0, c1, c2, 1.0f);
+}
+template <int FMT>
+__device__ __forceinline__ float4 decode_rgba(uint32_t p) {
+  const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p));
+  const float c2 = unorm8(byte_to_float<2>(p)), c3 = unorm8(byte_to_float<3>(p));
+  if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, c3);
+  return make_float4(c0, c1, c2, c3);
+}
+
+// TW  = shared tile row stride in texels (compile time, so every tap is base + immediate): 64 covers out->in
+//       scales up to 0.93 for a 64-wide output tile, 72 covers the rest up to 1.0.
+// TMA = the raw RGBA8 source box (tile + halo) arrives by one cp.async.bulk.tensor into shared memory and is
+//       decoded from there; otherwise (FP16/FP32 sources, unaligned pitch) texels are fetched with plain loads.
+template <int FIN, int FOUT, int TW, bool TMA>
+__global__ void __launch_bounds__(kThreads, 2) easu_kernel(const __grid_constant__ EasuArgs a,
+                                                           const __grid_constant__ CUtensorMap srcMap) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ uint64_t tileBar;
+  const int th = a.tileH, tn = TW * th;
+  float4 *sC = reinterpret_cast<float4 *>(smem_raw);  // decoded colour (r,g,b,1)
+  float4 *sF = sC + tn;                               // (dirX, dirY, lenX, lenY) per texel
+  float *sL = reinterpret_cast<float *>(sF + tn);     // luma*2 plane (conflict-free stencil reads)
+  uint32_t *sRaw = reinterpret_cast<uint32_t *>(sF);  // TMA landing zone; dead before the features are written
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH;
   // source tile origin: one texel left/above the 'f' texel of the tile's first pixel
   const int sx0 = (int)floorf(easu_pos(ox0, a.c0x, a.c0z)) - 1;
   const int sy0 = (int)floorf(easu_pos(oy0, a.c0y, a.c0w)) - 1;
+  const int tw = a.tileW; // columns actually needed (<= TW, multiple of 4)
+
+  if constexpr (TMA) {
+    if (tid == 0) {
+      mbar_init(&tileBar, 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(&tileBar, (uint32_t)(tw * th * 4));
+      tma_load_2d(sRaw, &srcMap, sx0, sy0, &tileBar);
+    }
+  }
 
   // this warp's 16x16 group and its radius test (warp-uniform)
   const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
   const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
 
   // ---- stage 1: decode the clamped source tile once ------------------------------------------
-  for (int ty = warp; ty < th; ty += kThreads / 32) {
-    const int gy = clampi(sy0 + ty, 0, a.src.h - 1);
-    const uint8_t *row = a.src.ptr + (size_t)gy * a.src.pitch;
-    for (int tx = lane; tx < tw; tx += 32) {
-      const int gx = clampi(sx0 + tx, 0, a.src.w - 1);
-      float4 c = fetch_texel<FIN>(row, gx);
-      const float l2 = c.z * 0.5f + (c.x * 0.5f + c.y); // luma*2, ffx_fsr1.h:363 (x0.5 is exact, so FMA-safe)
-      c.w = l2;
-      sC[ty * tw + tx] = c;
-      sL[ty * tw + tx] = l2;
+  if constexpr (TMA) {
+    __syncthreads();          // barrier initialised before anyone polls it
+    mbar_wait(&tileBar, 0);   // the box has landed (out-of-image texels are zero)
+    for (int ty = warp; ty < th; ty += kThreads / 32) {
+      const uint32_t *row = sRaw + (clampi(sy0 + ty, 0, a.src.h - 1) - sy0) * tw; // clamp-to-edge: re-read the edge row
+      for (int tx = lane; tx < tw; tx += 32) {
+        const float4 c = decode_rgb1<FIN>(row[clampi(sx0 + tx, 0, a.src.w - 1) - sx0]);
+        sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y); // luma*2, ffx_fsr1.h:363 (x0.5 is exact, so FMA-safe)
+        sC[ty * TW + tx] = c;
+      }
+    }
+  } else {
+    for (int ty = warp; ty < th; ty += kThreads / 32) {
+      const int gy = clampi(sy0 + ty, 0, a.src.h - 1);
+      const uint8_t *row = a.src.ptr + (size_t)gy * a.src.pitch;
+      for (int tx = lane; tx < tw; tx += 32) {
+        const int gx = clampi(sx0 + tx, 0, a.src.w - 1);
+        float4 c = fetch_texel<FIN>(row, gx);
+        sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y);
+        c.w = 1.0f; // EASU ignores source alpha; the fast path accumulates the tap weight through this lane
+        sC[ty * TW + tx] = c;
+      }
     }
   }
   const int anyInside = __syncthreads_or(inside);
@@ -248,9 +396,9 @@ __global__ void __launch_bounds__(kThreads, 2) easu_kernel(const EasuArgs a) {
   // ---- stage 2: per-source-texel direction/length features (only where EASU will run) ---------
   if (anyInside) {
     for (int ty = 1 + warp; ty < th - 1; ty += kThreads / 32) {
-      const float *l = sL + ty * tw;
+      const float *l = sL + ty * TW;
       for (int tx = 1 + lane; tx < tw - 1; tx += 32)
-        sF[ty * tw + tx] = easu_feature(l[tx - tw], l[tx - 1], l[tx], l[tx + 1], l[tx + tw]);
+        sF[ty * TW + tx] = easu_feature(l[tx - TW], l[tx - 1], l[tx], l[tx + 1], l[tx + TW]);
     }
     __syncthreads();
   }
@@ -258,33 +406,40 @@ __global__ void __launch_bounds__(kThreads, 2) easu_kernel(const EasuArgs a) {
   // ---- stage 3: one warp per 16x16 group, 8 pixels per lane ------------------------------------
   const int x = (int)ggx * 16 + (lane & 15);
   if (x >= a.dst.w) return;
-  const float ppx_full = easu_pos(x, a.c0x, a.c0z);
-  const float fpx = floorf(ppx_full);
-  const float ppx = ppx_full - fpx;
-  const int ix = (int)fpx - sx0;
+  const int yFirst = (int)ggy * 16 + (lane >> 4);
+  if (inside) {
+    const float ppx_full = easu_pos(x, a.c0x, a.c0z);
+    const float fpx = floorf(ppx_full);
+    const float ppx = ppx_full - fpx;
+    const int ix = (int)fpx - sx0;
 #pragma unroll 2
-  for (int k = 0; k < 8; ++k) {
-    const int y = (int)ggy * 16 + (lane >> 4) + 2 * k;
-    if (y >= a.dst.h) break;
-    float3 c;
-    if (inside) {
+    for (int k = 0; k < 8; ++k) {
+      const int y = yFirst + 2 * k;
+      if (y >= a.dst.h) break;
       const float ppy_full = easu_pos(y, a.c0y, a.c0w);
       const float fpy = floorf(ppy_full);
-      c = easu_filter(sC, sF, tw, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
-    } else {
-      c = easu_bilinear(sC, tw, th, sx0, sy0, x, y, a);
+      float3 c;
+      if constexpr (kStrict) c = easu_filter(sC, sF, TW, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
+      else c = easu_filter_fast<TW>(sC, sF, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
+      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
     }
-    store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+  } else {
+    for (int k = 0; k < 8; ++k) {
+      const int y = yFirst + 2 * k;
+      if (y >= a.dst.h) break;
+      const float3 c = easu_bilinear(sC, TW, th, sx0, sy0, x, y, a);
+      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // RCAS
 // ------------------------------------------------------------------------------------------------
-constexpr int kRcasTW = kTileW + 4; // 1-texel halo each side, padded to a multiple of 4 texels
+constexpr int kRcasTW = kTileW + 4; // 1-texel halo each side, padded to a multiple of 4 texels (TMA box width)
 constexpr int kRcasTH = kTileH + 2;
 
-// FsrRcasF, ffx_fsr1.h:684-769 (FSR_RCAS_DENOISE / PASSTHROUGH_ALPHA undefined: fsr_rcas.hlsl:1-4)
+// FsrRcasF, ffx_fsr1.h:684-769 (FSR_RCAS_DENOISE / PASSTHROUGH_ALPHA undefined: fsr_rcas.hlsl:1-4), reference order
 __device__ __forceinline__ float3 rcas_filter(const float4 b, const float4 d, const float4 e, const float4 f,
                                               const float4 h, float sharp) {
   const float mn4R = fminf(fminf(b.x, fminf(d.x, f.x)), h.x), mx4R = fmaxf(fmaxf(b.x, fmaxf(d.x, f.x)), h.x);
@@ -306,45 +461,100 @@ __device__ __forceinline__ float3 rcas_filter(const float4 b, const float4 d, co
                      (lobe * b.z + lobe * d.z + lobe * h.z + lobe * f.z + e.z) * rcpL);
 }
 
-template <int FIN, int FOUT>
-__global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const RcasArgs a) {
-  __shared__ __align__(16) float4 sC[kRcasTH * kRcasTW];
+// fast math: (r,g) ride the FP32x2 pipe, b stays scalar; lobe*(b+d+h+f)+e regrouped
+__device__ __forceinline__ float3 rcas_filter_fast(const float4 b, const float4 d, const float4 e, const float4 f,
+                                                   const float4 h, float sharp) {
+  const float mn4R = fminf(fminf(b.x, fminf(d.x, f.x)), h.x), mx4R = fmaxf(fmaxf(b.x, fmaxf(d.x, f.x)), h.x);
+  const float mn4G = fminf(fminf(b.y, fminf(d.y, f.y)), h.y), mx4G = fmaxf(fmaxf(b.y, fmaxf(d.y, f.y)), h.y);
+  const float mn4B = fminf(fminf(b.z, fminf(d.z, f.z)), h.z), mx4B = fmaxf(fmaxf(b.z, fmaxf(d.z, f.z)), h.z);
+  const f2 mx = make_float2(mx4R, mx4G), mn = make_float2(mn4R, mn4G);
+  const f2 dMin = mul2(mx, bc(4.0f)), dMax = fma2(mn, bc(4.0f), bc(-4.0f));
+  const f2 hitMin = mul2(mn, make_float2(rcp_mode(dMin.x), rcp_mode(dMin.y)));
+  const f2 hitMax = mul2(add2(bc(1.0f), make_float2(-mx4R, -mx4G)), make_float2(rcp_mode(dMax.x), rcp_mode(dMax.y)));
+  const float hitMinB = mn4B * rcp_mode(4.0f * mx4B);
+  const float hitMaxB = (1.0f - mx4B) * rcp_mode(fmaf(4.0f, mn4B, -4.0f));
+  const float lobeR = fmaxf(-hitMin.x, hitMax.x), lobeG = fmaxf(-hitMin.y, hitMax.y), lobeB = fmaxf(-hitMinB, hitMaxB);
+  const float lobe =
+      fmaxf((float)(-(0.25 - (1.0 / 16.0))), fminf(fmaxf(lobeR, fmaxf(lobeG, lobeB)), 0.0f)) * sharp;
+  const float rcpL = prx_med_rcp(fmaf(4.0f, lobe, 1.0f));
+  const f2 sRG = add2(add2(make_float2(b.x, b.y), make_float2(d.x, d.y)), add2(make_float2(h.x, h.y), make_float2(f.x, f.y)));
+  const float sB = (b.z + d.z) + (h.z + f.z);
+  const f2 pRG = mul2(fma2(sRG, bc(lobe), make_float2(e.x, e.y)), bc(rcpL));
+  return make_float3(pRG.x, pRG.y, fmaf(lobe, sB, e.z) * rcpL);
+}
+
+__device__ __forceinline__ float3 rcas_filter_mode(const float4 b, const float4 d, const float4 e, const float4 f,
+                                                   const float4 h, float sharp) {
+  if constexpr (kStrict) return rcas_filter(b, d, e, f, h, sharp);
+  else return rcas_filter_fast(b, d, e, f, h, sharp);
+}
+
+// One CTA: 64x32 output pixels; the (66 x 34) source box arrives by TMA (zero fill outside the image is exactly
+// Texture2D.Load's behaviour) and is decoded once into a float4 tile.  One warp per 16x16 group; each lane walks a
+// column of 8 rows and keeps the b / e / h texels of the cross in registers, so a pixel costs 3 shared loads, not 5.
+template <int FIN, int FOUT, bool TMA>
+__global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant__ RcasArgs a,
+                                                           const __grid_constant__ CUtensorMap srcMap) {
+  __shared__ __align__(128) float4 sC[kRcasTH * kRcasTW];
+  __shared__ __align__(128) uint32_t sRaw[TMA ? kRcasTH * kRcasTW : 1];
+  __shared__ uint64_t tileBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH;
   const int sx0 = ox0 - 1, sy0 = oy0 - 1;
 
-  // decode tile + 1-texel ring; Texture2D.Load semantics: out of bounds reads 0 (fsr_rcas.hlsl:18)
-  for (int ty = warp; ty < kRcasTH; ty += kThreads / 32) {
-    const int gy = sy0 + ty;
-    const bool rowOk = gy >= 0 && gy < a.src.h;
-    const uint8_t *row = a.src.ptr + (size_t)(rowOk ? gy : 0) * a.src.pitch;
-    for (int tx = lane; tx < kTileW + 2; tx += 32) {
-      const int gx = sx0 + tx;
-      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rowOk && gx >= 0 && gx < a.src.w) c = fetch_texel<FIN>(row, gx);
-      sC[ty * kRcasTW + tx] = c;
+  if constexpr (TMA) {
+    if (tid == 0) {
+      mbar_init(&tileBar, 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(&tileBar, (uint32_t)(kRcasTH * kRcasTW * 4));
+      tma_load_2d(sRaw, &srcMap, sx0, sy0, &tileBar);
+    }
+  }
+  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
+  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
+
+  if constexpr (TMA) {
+    __syncthreads();
+    mbar_wait(&tileBar, 0);
+    for (int q = tid; q < kRcasTH * kRcasTW; q += kThreads) sC[q] = decode_rgba<FIN>(sRaw[q]);
+  } else {
+    // Texture2D.Load semantics: out of bounds reads 0 (fsr_rcas.hlsl:18)
+    for (int ty = warp; ty < kRcasTH; ty += kThreads / 32) {
+      const int gy = sy0 + ty;
+      const bool rowOk = gy >= 0 && gy < a.src.h;
+      const uint8_t *row = a.src.ptr + (size_t)(rowOk ? gy : 0) * a.src.pitch;
+      for (int tx = lane; tx < kTileW + 2; tx += 32) {
+        const int gx = sx0 + tx;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rowOk && gx >= 0 && gx < a.src.w) c = fetch_texel<FIN>(row, gx);
+        sC[ty * kRcasTW + tx] = c;
+      }
     }
   }
   __syncthreads();
 
-  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
-  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
   const int x = (int)ggx * 16 + (lane & 15);
   if (x >= a.dst.w) return;
-  const int tx = x - sx0;
-#pragma unroll 2
-  for (int k = 0; k < 8; ++k) {
-    const int y = (int)ggy * 16 + (lane >> 4) + 2 * k;
-    if (y >= a.dst.h) break;
-    const float4 *p = sC + (y - sy0) * kRcasTW + tx;
-    const float4 e = p[0];
-    uint8_t *drow = a.dst.ptr + (size_t)y * a.dst.pitch;
-    if (inside) {
-      const float3 c = rcas_filter(p[-kRcasTW], p[-1], e, p[1], p[kRcasTW], a.sharp);
-      store_texel<FOUT>(drow, x, c.x, c.y, c.z, 1.0f);
-    } else {
-      // OutputTexture[p] = mul * InputTexture[p], alpha included (fsr_rcas.hlsl:45-53)
-      store_texel<FOUT>(drow, x, 1.0f * e.x, a.tintGB * e.y, a.tintGB * e.z, 1.0f * e.w);
+  const int y0 = (int)ggy * 16 + (lane >> 4) * 8; // this lane's 8 consecutive rows
+  const float4 *p = sC + (y0 - sy0) * kRcasTW + (x - sx0);
+  if (inside) {
+    float4 b = p[-kRcasTW], e = p[0];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int y = y0 + k;
+      if (y >= a.dst.h) break;
+      const float4 h = p[kRcasTW], d = p[-1], f = p[1];
+      const float3 c = rcas_filter_mode(b, d, e, f, h, a.sharp);
+      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+      b = e; e = h; p += kRcasTW;
+    }
+  } else {
+    // OutputTexture[p] = mul * InputTexture[p], alpha included (fsr_rcas.hlsl:45-53)
+    for (int k = 0; k < 8; ++k) {
+      const int y = y0 + k;
+      if (y >= a.dst.h) break;
+      const float4 e = p[k * kRcasTW];
+      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, 1.0f * e.x, a.tintGB * e.y, a.tintGB * e.z, 1.0f * e.w);
     }
   }
 }
