@@ -357,8 +357,9 @@ __global__ void __launch_bounds__(kThreads, 2) easu_kernel(const __grid_constant
     if (tid == 0) {
       mbar_init(&tileBar, 1);
       fence_barrier_init();
-      mbar_arrive_expect_tx(&tileBar, (uint32_t)(tw * th * 4));
-      tma_load_2d(sRaw, &srcMap, sx0, sy0, &tileBar);
+      // the box origin must be 16-byte aligned in x (4 texels): load from floor4(sx0), (tw + 4) columns wide
+      mbar_arrive_expect_tx(&tileBar, (uint32_t)((tw + 4) * th * 4));
+      tma_load_2d(sRaw, &srcMap, sx0 & ~3, sy0, &tileBar);
     }
   }
 
@@ -370,10 +371,11 @@ __global__ void __launch_bounds__(kThreads, 2) easu_kernel(const __grid_constant
   if constexpr (TMA) {
     __syncthreads();          // barrier initialised before anyone polls it
     mbar_wait(&tileBar, 0);   // the box has landed (out-of-image texels are zero)
+    const int rawW = tw + 4, rx0 = sx0 & ~3;
     for (int ty = warp; ty < th; ty += kThreads / 32) {
-      const uint32_t *row = sRaw + (clampi(sy0 + ty, 0, a.src.h - 1) - sy0) * tw; // clamp-to-edge: re-read the edge row
+      const uint32_t *row = sRaw + (clampi(sy0 + ty, 0, a.src.h - 1) - sy0) * rawW; // clamp-to-edge: re-read the edge row
       for (int tx = lane; tx < tw; tx += 32) {
-        const float4 c = decode_rgb1<FIN>(row[clampi(sx0 + tx, 0, a.src.w - 1) - sx0]);
+        const float4 c = decode_rgb1<FIN>(row[clampi(sx0 + tx, 0, a.src.w - 1) - rx0]);
         sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y); // luma*2, ffx_fsr1.h:363 (x0.5 is exact, so FMA-safe)
         sC[ty * TW + tx] = c;
       }
@@ -436,8 +438,9 @@ __global__ void __launch_bounds__(kThreads, 2) easu_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // RCAS
 // ------------------------------------------------------------------------------------------------
-constexpr int kRcasTW = kTileW + 4; // 1-texel halo each side, padded to a multiple of 4 texels (TMA box width)
+constexpr int kRcasTW = kTileW + 4;  // float tile: 1-texel halo each side, padded to a multiple of 4 texels
 constexpr int kRcasTH = kTileH + 2;
+constexpr int kRcasRawW = kTileW + 8; // TMA box: starts 4 texels left of the tile (16-byte aligned origin), 1 used right
 
 // FsrRcasF, ffx_fsr1.h:684-769 (FSR_RCAS_DENOISE / PASSTHROUGH_ALPHA undefined: fsr_rcas.hlsl:1-4), reference order
 __device__ __forceinline__ float3 rcas_filter(const float4 b, const float4 d, const float4 e, const float4 f,
@@ -496,7 +499,7 @@ template <int FIN, int FOUT, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant__ RcasArgs a,
                                                            const __grid_constant__ CUtensorMap srcMap) {
   __shared__ __align__(128) float4 sC[kRcasTH * kRcasTW];
-  __shared__ __align__(128) uint32_t sRaw[TMA ? kRcasTH * kRcasTW : 1];
+  __shared__ __align__(128) uint32_t sRaw[TMA ? kRcasTH * kRcasRawW : 1];
   __shared__ uint64_t tileBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH;
@@ -506,8 +509,8 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
     if (tid == 0) {
       mbar_init(&tileBar, 1);
       fence_barrier_init();
-      mbar_arrive_expect_tx(&tileBar, (uint32_t)(kRcasTH * kRcasTW * 4));
-      tma_load_2d(sRaw, &srcMap, sx0, sy0, &tileBar);
+      mbar_arrive_expect_tx(&tileBar, (uint32_t)(kRcasTH * kRcasRawW * 4));
+      tma_load_2d(sRaw, &srcMap, ox0 - 4, sy0, &tileBar); // x origin 16-byte aligned: 3 unused texels on the left
     }
   }
   const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
@@ -516,7 +519,8 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
   if constexpr (TMA) {
     __syncthreads();
     mbar_wait(&tileBar, 0);
-    for (int q = tid; q < kRcasTH * kRcasTW; q += kThreads) sC[q] = decode_rgba<FIN>(sRaw[q]);
+    for (int ty = warp; ty < kRcasTH; ty += kThreads / 32)
+      for (int tx = lane; tx < kTileW + 2; tx += 32) sC[ty * kRcasTW + tx] = decode_rgba<FIN>(sRaw[ty * kRcasRawW + tx + 3]);
   } else {
     // Texture2D.Load semantics: out of bounds reads 0 (fsr_rcas.hlsl:18)
     for (int ty = warp; ty < kRcasTH; ty += kThreads / 32) {
