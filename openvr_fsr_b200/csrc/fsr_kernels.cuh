@@ -332,106 +332,174 @@ __device__ __forceinline__ float4 decode_rgba(uint32_t p) {
 }
 
 // TW  = shared tile row stride in texels (compile time, so every tap is base + immediate): 64 covers out->in
-//       scales up to 0.93 for a 64-wide output tile, 72 covers the rest up to 1.0.
-// TMA = the raw RGBA8 source box (tile + halo) arrives by one cp.async.bulk.tensor into shared memory and is
-//       decoded from there; otherwise (FP16/FP32 sources, unaligned pitch) texels are fetched with plain loads.
+//       scales up to 0.87 for a 64-wide output tile, 72 covers the rest up to 1.0.
+// TMA = the raw RGBA8 source box (tile + halo) arrives by cp.async.bulk.tensor into a double-buffered landing zone
+//       and is decoded from there; otherwise (FP16/FP32 sources, unaligned pitch) texels are fetched with plain loads.
+// Persistent: the grid is (CTAs per SM) x (SM count); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... in
+// row-major order and, in the TMA variant, has the NEXT tile's box in flight while it works on the current one.
+constexpr int kEasuRowsPerThread = 5;  // tile rows handled by one warp: ceil(37 / 8)
+constexpr int kEasuColsPerThread = 3;  // 32-wide column blocks: ceil(72 / 32)
+
 template <int FIN, int FOUT, int TW, bool TMA>
-__global__ void __launch_bounds__(kThreads, 2) easu_kernel(const __grid_constant__ EasuArgs a,
+__global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant__ EasuArgs a,
                                                            const __grid_constant__ CUtensorMap srcMap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ uint64_t tileBar;
+  __shared__ uint64_t tileBar[2];
   const int th = a.tileH, tn = TW * th;
   float4 *sC = reinterpret_cast<float4 *>(smem_raw);  // decoded colour (r,g,b,1)
   float4 *sF = sC + tn;                               // (dirX, dirY, lenX, lenY) per texel
   float *sL = reinterpret_cast<float *>(sF + tn);     // luma*2 plane (conflict-free stencil reads)
-  uint32_t *sRaw = reinterpret_cast<uint32_t *>(sF);  // TMA landing zone; dead before the features are written
+  const int rawW = a.tileW + 4;                       // TMA box width (origin floored to 4 texels)
+  const int rawN = (rawW * th + 31) & ~31;            // per-buffer size in texels, keeps buffer 1 128-byte aligned
+  uint32_t *sRaw = reinterpret_cast<uint32_t *>(smem_raw + ((tn * 36 + 127) & ~127)); // [2][rawN] landing zones (TMA only), 128-byte aligned
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH;
-  // source tile origin: one texel left/above the 'f' texel of the tile's first pixel
-  const int sx0 = (int)floorf(easu_pos(ox0, a.c0x, a.c0z)) - 1;
-  const int sy0 = (int)floorf(easu_pos(oy0, a.c0y, a.c0w)) - 1;
-  const int tw = a.tileW; // columns actually needed (<= TW, multiple of 4)
+  const int tilesX = (a.dst.w + kTileW - 1) / kTileW, tilesY = (a.dst.h + kTileH - 1) / kTileH;
+  const int numTiles = tilesX * tilesY;
 
+  auto tile_origin = [&](int t, int &ox0, int &oy0, int &sx0, int &sy0) {
+    const int ty = t / tilesX, tx = t - ty * tilesX;
+    ox0 = tx * kTileW; oy0 = ty * kTileH;
+    // source tile origin: one texel left/above the 'f' texel of the tile's first pixel
+    sx0 = (int)floorf(easu_pos(ox0, a.c0x, a.c0z)) - 1;
+    sy0 = (int)floorf(easu_pos(oy0, a.c0y, a.c0w)) - 1;
+  };
+
+  int t = blockIdx.x;
   if constexpr (TMA) {
     if (tid == 0) {
-      mbar_init(&tileBar, 1);
+      mbar_init(&tileBar[0], 1);
+      mbar_init(&tileBar[1], 1);
       fence_barrier_init();
-      // the box origin must be 16-byte aligned in x (4 texels): load from floor4(sx0), (tw + 4) columns wide
-      mbar_arrive_expect_tx(&tileBar, (uint32_t)((tw + 4) * th * 4));
-      tma_load_2d(sRaw, &srcMap, sx0 & ~3, sy0, &tileBar);
-    }
-  }
-
-  // this warp's 16x16 group and its radius test (warp-uniform)
-  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
-  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
-
-  // ---- stage 1: decode the clamped source tile once ------------------------------------------
-  if constexpr (TMA) {
-    __syncthreads();          // barrier initialised before anyone polls it
-    mbar_wait(&tileBar, 0);   // the box has landed (out-of-image texels are zero)
-    const int rawW = tw + 4, rx0 = sx0 & ~3;
-    for (int ty = warp; ty < th; ty += kThreads / 32) {
-      const uint32_t *row = sRaw + (clampi(sy0 + ty, 0, a.src.h - 1) - sy0) * rawW; // clamp-to-edge: re-read the edge row
-      for (int tx = lane; tx < tw; tx += 32) {
-        const float4 c = decode_rgb1<FIN>(row[clampi(sx0 + tx, 0, a.src.w - 1) - rx0]);
-        sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y); // luma*2, ffx_fsr1.h:363 (x0.5 is exact, so FMA-safe)
-        sC[ty * TW + tx] = c;
+      if (t < numTiles) {
+        int ox0, oy0, sx0, sy0;
+        tile_origin(t, ox0, oy0, sx0, sy0);
+        mbar_arrive_expect_tx(&tileBar[0], (uint32_t)(rawW * th * 4));
+        tma_load_2d(sRaw, &srcMap, sx0 & ~3, sy0, &tileBar[0]); // box origin 16-byte aligned in x
       }
-    }
-  } else {
-    for (int ty = warp; ty < th; ty += kThreads / 32) {
-      const int gy = clampi(sy0 + ty, 0, a.src.h - 1);
-      const uint8_t *row = a.src.ptr + (size_t)gy * a.src.pitch;
-      for (int tx = lane; tx < tw; tx += 32) {
-        const int gx = clampi(sx0 + tx, 0, a.src.w - 1);
-        float4 c = fetch_texel<FIN>(row, gx);
-        sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y);
-        c.w = 1.0f; // EASU ignores source alpha; the fast path accumulates the tap weight through this lane
-        sC[ty * TW + tx] = c;
-      }
-    }
-  }
-  const int anyInside = __syncthreads_or(inside);
-
-  // ---- stage 2: per-source-texel direction/length features (only where EASU will run) ---------
-  if (anyInside) {
-    for (int ty = 1 + warp; ty < th - 1; ty += kThreads / 32) {
-      const float *l = sL + ty * TW;
-      for (int tx = 1 + lane; tx < tw - 1; tx += 32)
-        sF[ty * TW + tx] = easu_feature(l[tx - TW], l[tx - 1], l[tx], l[tx + 1], l[tx + TW]);
     }
     __syncthreads();
   }
 
-  // ---- stage 3: one warp per 16x16 group, 8 pixels per lane ------------------------------------
-  const int x = (int)ggx * 16 + (lane & 15);
-  if (x >= a.dst.w) return;
-  const int yFirst = (int)ggy * 16 + (lane >> 4);
-  if (inside) {
-    const float ppx_full = easu_pos(x, a.c0x, a.c0z);
-    const float fpx = floorf(ppx_full);
-    const float ppx = ppx_full - fpx;
-    const int ix = (int)fpx - sx0;
+  uint32_t buf = 0, phaseBits = 0;
+  for (; t < numTiles; t += gridDim.x) {
+    int ox0, oy0, sx0, sy0;
+    tile_origin(t, ox0, oy0, sx0, sy0);
+    // float-tile origin and width in source texels: the TMA variant keeps the box's aligned origin
+    const int tx0 = TMA ? (sx0 & ~3) : sx0;
+    const int cols = TMA ? rawW : a.tileW;
+
+    // this warp's 16x16 group and its radius test (warp-uniform)
+    const uint32_t ggx = (uint32_t)(ox0 >> 4) + (warp & 3), ggy = (uint32_t)(oy0 >> 4) + (warp >> 2);
+    const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
+
+    // ---- stage 1: decode the clamped source tile once, loads batched per thread for ILP -------------
+    if constexpr (TMA) {
+      mbar_wait(&tileBar[buf], (phaseBits >> buf) & 1u); // this tile's box has landed (zeros outside the image)
+      phaseBits ^= 1u << buf;
+      const int tn2 = t + gridDim.x;
+      if (tid == 0 && tn2 < numTiles) { // prefetch the next tile into the other buffer (free since the last decode)
+        int nox, noy, nsx, nsy;
+        tile_origin(tn2, nox, noy, nsx, nsy);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&tileBar[buf ^ 1], (uint32_t)(rawW * th * 4));
+        tma_load_2d(sRaw + (buf ^ 1) * rawN, &srcMap, nsx & ~3, nsy, &tileBar[buf ^ 1]);
+      }
+      const uint32_t *raw = sRaw + buf * rawN;
+#pragma unroll
+      for (int i = 0; i < kEasuColsPerThread; ++i) {
+        const int tx = lane + 32 * i;
+        if (tx < cols) {
+          const int rcol = clampi(tx0 + tx, 0, a.src.w - 1) - tx0; // clamp-to-edge: re-read the edge column / row
+          uint32_t px[kEasuRowsPerThread];
+#pragma unroll
+          for (int j = 0; j < kEasuRowsPerThread; ++j) {
+            const int ty = warp + 8 * j;
+            px[j] = ty < th ? raw[(clampi(sy0 + ty, 0, a.src.h - 1) - sy0) * rawW + rcol] : 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < kEasuRowsPerThread; ++j) {
+            const int ty = warp + 8 * j;
+            if (ty < th) {
+              const float4 c = decode_rgb1<FIN>(px[j]);
+              sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y); // luma*2, ffx_fsr1.h:363 (x0.5 exact: FMA-safe)
+              sC[ty * TW + tx] = c;
+            }
+          }
+        }
+      }
+    } else {
+      for (int ty = warp; ty < th; ty += kThreads / 32) {
+        const int gy = clampi(sy0 + ty, 0, a.src.h - 1);
+        const uint8_t *row = a.src.ptr + (size_t)gy * a.src.pitch;
+        for (int tx = lane; tx < cols; tx += 32) {
+          const int gx = clampi(tx0 + tx, 0, a.src.w - 1);
+          float4 c = fetch_texel<FIN>(row, gx);
+          sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y);
+          c.w = 1.0f; // EASU ignores source alpha; the fast path accumulates the tap weight through this lane
+          sC[ty * TW + tx] = c;
+        }
+      }
+    }
+    const int anyInside = __syncthreads_or(inside);
+
+    // ---- stage 2: per-source-texel direction/length features (only where EASU will run) -----------
+    if (anyInside) {
+#pragma unroll
+      for (int i = 0; i < kEasuColsPerThread; ++i) {
+        const int tx = 1 + lane + 32 * i;
+        if (tx < cols - 1) {
+          float lA[kEasuRowsPerThread], lB[kEasuRowsPerThread], lC[kEasuRowsPerThread], lD[kEasuRowsPerThread],
+              lE[kEasuRowsPerThread];
+#pragma unroll
+          for (int j = 0; j < kEasuRowsPerThread; ++j) {
+            const int ty = 1 + warp + 8 * j;
+            if (ty < th - 1) {
+              const float *l = sL + ty * TW + tx;
+              lA[j] = l[-TW]; lB[j] = l[-1]; lC[j] = l[0]; lD[j] = l[1]; lE[j] = l[TW];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kEasuRowsPerThread; ++j) {
+            const int ty = 1 + warp + 8 * j;
+            if (ty < th - 1) sF[ty * TW + tx] = easu_feature(lA[j], lB[j], lC[j], lD[j], lE[j]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- stage 3: one warp per 16x16 group, 8 pixels per lane --------------------------------------
+    const int x = (int)ggx * 16 + (lane & 15);
+    if (x < a.dst.w) {
+      const int yFirst = (int)ggy * 16 + (lane >> 4);
+      if (inside) {
+        const float ppx_full = easu_pos(x, a.c0x, a.c0z);
+        const float fpx = floorf(ppx_full);
+        const float ppx = ppx_full - fpx;
+        const int ix = (int)fpx - tx0;
 #pragma unroll 2
-    for (int k = 0; k < 8; ++k) {
-      const int y = yFirst + 2 * k;
-      if (y >= a.dst.h) break;
-      const float ppy_full = easu_pos(y, a.c0y, a.c0w);
-      const float fpy = floorf(ppy_full);
-      float3 c;
-      if constexpr (kStrict) c = easu_filter(sC, sF, TW, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
-      else c = easu_filter_fast<TW>(sC, sF, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
-      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+        for (int k = 0; k < 8; ++k) {
+          const int y = yFirst + 2 * k;
+          if (y >= a.dst.h) break;
+          const float ppy_full = easu_pos(y, a.c0y, a.c0w);
+          const float fpy = floorf(ppy_full);
+          float3 c;
+          if constexpr (kStrict) c = easu_filter(sC, sF, TW, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
+          else c = easu_filter_fast<TW>(sC, sF, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
+          store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+        }
+      } else {
+        for (int k = 0; k < 8; ++k) {
+          const int y = yFirst + 2 * k;
+          if (y >= a.dst.h) break;
+          const float3 c = easu_bilinear(sC, TW, th, tx0, sy0, x, y, a);
+          store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+        }
+      }
     }
-  } else {
-    for (int k = 0; k < 8; ++k) {
-      const int y = yFirst + 2 * k;
-      if (y >= a.dst.h) break;
-      const float3 c = easu_bilinear(sC, TW, th, sx0, sy0, x, y, a);
-      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
-    }
+    __syncthreads(); // every warp is done with this tile before the next decode overwrites it
+    buf ^= 1u;
   }
 }
 

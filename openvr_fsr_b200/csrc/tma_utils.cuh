@@ -44,6 +44,8 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+// order this thread's prior generic-proxy accesses to shared memory before subsequent async-proxy (TMA) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
