@@ -207,8 +207,9 @@ def main():
     base_l, base_r = synth.stereo_pair("natural", IN_W, IN_H, 1)
     for i in range(args.pool):
         sh = 37 * (i + rank * args.pool)
-        pool.append((torch.from_numpy(np.roll(base_l, sh, axis=0)).to(dev),
-                     torch.from_numpy(np.roll(base_r, sh, axis=0)).to(dev)))
+        # device images with a 256-byte-aligned row pitch (what cudaMallocPitch / ovrfsr_image_alloc return): the
+        # TMA tile loader needs a 16-byte-aligned pitch; algorithmic bytes are counted without the padding
+        pool.append((ovr.to_image(np.roll(base_l, sh, axis=0), dev), ovr.to_image(np.roll(base_r, sh, axis=0), dev)))
     pp = ovr.PostProcessor(cfg)
     assert np.array_equal(pp_consts_after_first(pp, pool[0][0]), consts["upscale"][0]), "rank constants differ from root's"
 
@@ -280,7 +281,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "radius": args.radius, "pairs_per_step_per_gpu": args.pool,
-                       "math": args.math, "l2": f"inputs larger than L2 ({args.pool} distinct pairs = "
+                       "math": args.math, "source_pitch": "256-byte aligned rows (TMA tile loads)", "l2": f"inputs larger than L2 ({args.pool} distinct pairs = "
                        f"{args.pool * 2 * IN_W * IN_H * 4 / 1e6:.0f} MB per GPU per step)",
                        "parallelism": f"frames sharded {world}x, no data-path collective"},
             "hbm_gbs_whole_pass": value / world * PAIR_BYTES / 1e9,
@@ -315,8 +316,8 @@ def per_kernel_times(ovr, pool, consts, math_mode, reps):
     """Mean device time of one EASU and one RCAS launch (per eye), events recorded on the launching stream."""
     import torch
     dev = pool[0][0].device
-    mid = torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8, device=dev)
-    dst = torch.empty_like(mid)
+    mid = ovr.alloc_image(OUT_W, OUT_H, torch.uint8, dev)
+    dst = ovr.alloc_image(OUT_W, OUT_H, torch.uint8, dev)
     marks = []  # (e0, e1, e2) per eye; nothing synchronises inside the loop, so the GPU stays busy
     for _ in range(reps):
         for left, right in pool:
@@ -360,7 +361,7 @@ def e2e_run(ovr, torch, dist, cfg, pool, dev, world, steps, warmup):
     copy engines and the SMs overlap."""
     pp = ovr.PostProcessor(cfg)
     n = len(pool)
-    h_in = [(l.cpu().pin_memory(), r.cpu().pin_memory()) for l, r in pool]
+    h_in = [(l.cpu().contiguous().pin_memory(), r.cpu().contiguous().pin_memory()) for l, r in pool]
     h_out = [(torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8).pin_memory(),
               torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8).pin_memory()) for _ in range(n)]
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]

@@ -71,6 +71,29 @@ def image_of(t, fmt: int | None = None) -> L.Image:
                    _format_of(t) if fmt is None else fmt, 1, 0)
 
 
+def alloc_image(width: int, height: int, dtype=None, device="cuda", align: int = 256):
+    """A (H, W, 4) device tensor whose row pitch is a multiple of `align` bytes -- what cudaMallocPitch /
+    ovrfsr_image_alloc give, and what the TMA tile loader needs (base and pitch 16-byte aligned).  The padding
+    bytes are never read or written by the kernels."""
+    import torch
+    dtype = dtype or torch.uint8
+    esize = torch.empty((), dtype=dtype).element_size()
+    row = width * 4 * esize
+    pitch = (row + align - 1) // align * align
+    buf = torch.zeros((height, pitch // esize), dtype=dtype, device=device)
+    return buf[:, : width * 4].view(height, width, 4) if pitch == row else torch.as_strided(
+        buf, (height, width, 4), (pitch // esize, 4, 1))
+
+
+def to_image(array, device="cuda", align: int = 256):
+    """Copy a numpy (H, W, 4) array into a pitch-aligned device image."""
+    import torch
+    src = torch.from_numpy(array)
+    img = alloc_image(array.shape[1], array.shape[0], src.dtype, device, align)
+    img.copy_(src)
+    return img
+
+
 def output_size(in_w: int, in_h: int, render_scale: float) -> tuple[int, int]:
     """PrepareResources, PostProcessor.cpp:509-518"""
     w, h = C.c_uint32(), C.c_uint32()

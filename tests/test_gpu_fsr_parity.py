@@ -108,3 +108,36 @@ def test_full_frame_c2_strict_bit_exact_and_fast_statistics(cuda):
         print(f"radius {radius}: fast per-pass mismatch EASU {(de > 0).mean():.2e} RCAS {(dr > 0).mean():.2e}; "
               f"composed: {(comp > 1).mean():.2e} of channel values beyond 1 LSB, max {comp.max()}")
         assert (comp > 1).mean() < 1e-3
+
+
+@pytest.mark.parametrize("iw,ih,scale", [(33, 47, 0.75), (211, 157, 0.75), (129, 65, 0.59), (100, 40, 1.0 / 1.07), (77, 50, 0.5)])
+def test_tma_and_plain_loaders_agree(cuda, iw, ih, scale):
+    """The same eye through the TMA tile loader (pitch-aligned image) and the plain-load fallback (tight pitch,
+    odd width): both bit-identical to the oracle in strict mode, identical to each other in fast mode."""
+    import torch
+    import openvr_fsr_b200 as ovr
+    from openvr_fsr_b200 import synth
+    from oracle import pyoracle as po
+    ow, oh = po.output_size(iw, ih, scale)
+    src = synth.natural_rgba8(iw, ih, 7)
+    for radius in (2.0, 0.45):
+        uc = po.upscale_constants(0, True, iw, ih, ow, oh, radius=radius)
+        sc = po.sharpen_constants(0, True, ow, oh, radius=radius, sharpness=0.8)
+        easu = po.easu(src, ow, oh, uc)
+        rcas = po.rcas(easu, sc)
+        tight_src, tight_mid = torch.from_numpy(src).to(cuda), torch.from_numpy(easu).to(cuda)
+        pitched_src, pitched_mid = ovr.to_image(src, cuda), ovr.to_image(easu, cuda)
+        assert pitched_src.stride(0) % 16 == 0
+        outs = {}
+        for mode in (ovr.MATH_STRICT, ovr.MATH_FAST):
+            for name, s_, m_ in (("tight", tight_src, tight_mid), ("pitched", pitched_src, pitched_mid)):
+                e = ovr.alloc_image(ow, oh, torch.uint8, cuda) if name == "pitched" else torch.empty((oh, ow, 4), dtype=torch.uint8, device=cuda)
+                r = torch.empty((oh, ow, 4), dtype=torch.uint8, device=cuda)
+                ovr.fsr_easu(s_, e, uc.words(), mode)
+                ovr.fsr_rcas(m_, r, sc.words(), mode)
+                torch.cuda.synchronize()
+                outs[(mode, name)] = (e.cpu().numpy(), r.cpu().numpy())
+        for name in ("tight", "pitched"):
+            assert np.array_equal(outs[(ovr.MATH_STRICT, name)][0], easu) and np.array_equal(outs[(ovr.MATH_STRICT, name)][1], rcas)
+        assert np.array_equal(outs[(ovr.MATH_FAST, "tight")][0], outs[(ovr.MATH_FAST, "pitched")][0])
+        assert np.array_equal(outs[(ovr.MATH_FAST, "tight")][1], outs[(ovr.MATH_FAST, "pitched")][1])
