@@ -331,8 +331,8 @@ __device__ __forceinline__ float4 decode_rgba(uint32_t p) {
   return make_float4(c0, c1, c2, c3);
 }
 
-// TW  = shared tile row stride in texels (compile time, so every tap is base + immediate): 64 covers out->in
-//       scales up to 0.87 for a 64-wide output tile, 72 covers the rest up to 1.0.
+// TW  = shared tile row stride in texels (compile time, so every tap is base + immediate): 60 covers out->in
+//       scales up to 0.81 for a 64-wide output tile (60 texels incl. the 4 TMA alignment columns), 72 the rest up to 1.0.
 // TMA = the raw RGBA8 source box (tile + halo) arrives by cp.async.bulk.tensor into a double-buffered landing zone
 //       and is decoded from there; otherwise (FP16/FP32 sources, unaligned pitch) texels are fetched with plain loads.
 // Persistent: the grid is (CTAs per SM) x (SM count); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... in
@@ -344,14 +344,13 @@ template <int FIN, int FOUT, int TW, bool TMA>
 __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant__ EasuArgs a,
                                                            const __grid_constant__ CUtensorMap srcMap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ uint64_t tileBar[2];
+  __shared__ uint64_t tileBar;
   const int th = a.tileH, tn = TW * th;
   float4 *sC = reinterpret_cast<float4 *>(smem_raw);  // decoded colour (r,g,b,1)
   float4 *sF = sC + tn;                               // (dirX, dirY, lenX, lenY) per texel
   float *sL = reinterpret_cast<float *>(sF + tn);     // luma*2 plane (conflict-free stencil reads)
   const int rawW = a.tileW + 4;                       // TMA box width (origin floored to 4 texels)
-  const int rawN = (rawW * th + 31) & ~31;            // per-buffer size in texels, keeps buffer 1 128-byte aligned
-  uint32_t *sRaw = reinterpret_cast<uint32_t *>(smem_raw + ((tn * 36 + 127) & ~127)); // [2][rawN] landing zones (TMA only), 128-byte aligned
+  uint32_t *sRaw = reinterpret_cast<uint32_t *>(smem_raw + ((tn * 36 + 127) & ~127)); // landing zone (TMA only), 128-byte aligned
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tilesX = (a.dst.w + kTileW - 1) / kTileW, tilesY = (a.dst.h + kTileH - 1) / kTileH;
@@ -368,20 +367,19 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
   int t = blockIdx.x;
   if constexpr (TMA) {
     if (tid == 0) {
-      mbar_init(&tileBar[0], 1);
-      mbar_init(&tileBar[1], 1);
+      mbar_init(&tileBar, 1);
       fence_barrier_init();
       if (t < numTiles) {
         int ox0, oy0, sx0, sy0;
         tile_origin(t, ox0, oy0, sx0, sy0);
-        mbar_arrive_expect_tx(&tileBar[0], (uint32_t)(rawW * th * 4));
-        tma_load_2d(sRaw, &srcMap, sx0 & ~3, sy0, &tileBar[0]); // box origin 16-byte aligned in x
+        mbar_arrive_expect_tx(&tileBar, (uint32_t)(rawW * th * 4));
+        tma_load_2d(sRaw, &srcMap, sx0 & ~3, sy0, &tileBar); // box origin 16-byte aligned in x
       }
     }
     __syncthreads();
   }
 
-  uint32_t buf = 0, phaseBits = 0;
+  uint32_t phase = 0;
   for (; t < numTiles; t += gridDim.x) {
     int ox0, oy0, sx0, sy0;
     tile_origin(t, ox0, oy0, sx0, sy0);
@@ -395,17 +393,9 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
 
     // ---- stage 1: decode the clamped source tile once, loads batched per thread for ILP -------------
     if constexpr (TMA) {
-      mbar_wait(&tileBar[buf], (phaseBits >> buf) & 1u); // this tile's box has landed (zeros outside the image)
-      phaseBits ^= 1u << buf;
-      const int tn2 = t + gridDim.x;
-      if (tid == 0 && tn2 < numTiles) { // prefetch the next tile into the other buffer (free since the last decode)
-        int nox, noy, nsx, nsy;
-        tile_origin(tn2, nox, noy, nsx, nsy);
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&tileBar[buf ^ 1], (uint32_t)(rawW * th * 4));
-        tma_load_2d(sRaw + (buf ^ 1) * rawN, &srcMap, nsx & ~3, nsy, &tileBar[buf ^ 1]);
-      }
-      const uint32_t *raw = sRaw + buf * rawN;
+      mbar_wait(&tileBar, phase); // this tile's box has landed (zeros outside the image)
+      phase ^= 1u;
+      const uint32_t *raw = sRaw;
 #pragma unroll
       for (int i = 0; i < kEasuColsPerThread; ++i) {
         const int tx = lane + 32 * i;
@@ -442,6 +432,17 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
       }
     }
     const int anyInside = __syncthreads_or(inside);
+    if constexpr (TMA) {
+      // the landing zone is fully decoded: refill it with the NEXT tile's box while this tile is filtered
+      const int tn2 = t + gridDim.x;
+      if (tid == 0 && tn2 < numTiles) {
+        int nox, noy, nsx, nsy;
+        tile_origin(tn2, nox, noy, nsx, nsy);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&tileBar, (uint32_t)(rawW * th * 4));
+        tma_load_2d(sRaw, &srcMap, nsx & ~3, nsy, &tileBar);
+      }
+    }
 
     // ---- stage 2: per-source-texel direction/length features (only where EASU will run) -----------
     if (anyInside) {
@@ -499,7 +500,6 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
       }
     }
     __syncthreads(); // every warp is done with this tile before the next decode overwrites it
-    buf ^= 1u;
   }
 }
 
