@@ -68,6 +68,19 @@ __device__ __forceinline__ float unorm8(float v) {
   return __fmaf_rn(e, r, q);
 }
 
+// Fast-math decode of byte K: PRMT builds the float 2^23+v, one FFMA computes (2^23+v)*r - 2^23*r = fl(v*r) with a
+// single rounding (2^23*r is exact).  Differs from the correctly rounded v/255 by at most 1 ulp (126 of 256 codes);
+// strict math always uses unorm8().
+template <int K>
+__device__ __forceinline__ float byte_to_unorm_mode(uint32_t p) {
+  if constexpr (kStrict) {
+    return unorm8(byte_to_float<K>(p));
+  } else {
+    const float r = 1.0f / 255.0f;
+    return __fmaf_rn(u2f(__byte_perm(p, 0x4B000000u, 0x7540 | K)), r, -8388608.0f * r);
+  }
+}
+
 // texel fetch -> float4 rgba.  No bounds logic here.
 template <int FMT>
 __device__ __forceinline__ float4 fetch_texel(const uint8_t *__restrict__ row, int x) {
@@ -111,9 +124,23 @@ __device__ __forceinline__ void store_texel(uint8_t *__restrict__ row, int x, fl
     reinterpret_cast<uint32_t *>(row)[x] = p;
   }
 }
-template <int FMT>
+// opaque RGBA8 pixel from three floats.  Fast math rounds with the 2^23 magic add (FFMA + byte permutes, no F2I):
+// round-to-nearest-even instead of floor(x+0.5), identical except on exact .5 ties.
 __device__ __forceinline__ uint32_t pack_rgba8_opaque(float r, float g, float b) {
-  return to_unorm8(r) | (to_unorm8(g) << 8) | (to_unorm8(b) << 16) | 0xff000000u;
+  if constexpr (kStrict) {
+    return to_unorm8(r) | (to_unorm8(g) << 8) | (to_unorm8(b) << 16) | 0xff000000u;
+  } else {
+    const uint32_t rb = f2u(__fmaf_rn(__saturatef(r), 255.0f, 8388608.0f));
+    const uint32_t gb = f2u(__fmaf_rn(__saturatef(g), 255.0f, 8388608.0f));
+    const uint32_t bb = f2u(__fmaf_rn(__saturatef(b), 255.0f, 8388608.0f));
+    return __byte_perm(__byte_perm(rb, gb, 0x0040), bb, 0x0410) | 0xff000000u;
+  }
+}
+// store (r,g,b,1): the common case of every filter on this path
+template <int FMT>
+__device__ __forceinline__ void store_opaque(uint8_t *__restrict__ row, int x, float r, float g, float b) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGBA8) reinterpret_cast<uint32_t *>(row)[x] = pack_rgba8_opaque(r, g, b);
+  else store_texel<FMT>(row, x, r, g, b, 1.0f);
 }
 
 // Workgroup radius test (fsr_easu.hlsl:40-44, fsr_rcas.hlsl:31-35, NIS_Upscale.hlsl:98-101):

@@ -319,14 +319,14 @@ __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, i
 // 3-channel decode of a packed RGBA8/BGRA8 texel (EASU never reads source alpha: its output alpha is 1)
 template <int FMT>
 __device__ __forceinline__ float4 decode_rgb1(uint32_t p) {
-  const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p)), c2 = unorm8(byte_to_float<2>(p));
+  const float c0 = byte_to_unorm_mode<0>(p), c1 = byte_to_unorm_mode<1>(p), c2 = byte_to_unorm_mode<2>(p);
   if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, 1.0f);
   return make_float4(c0, c1, c2, 1.0f);
 }
 template <int FMT>
 __device__ __forceinline__ float4 decode_rgba(uint32_t p) {
-  const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p));
-  const float c2 = unorm8(byte_to_float<2>(p)), c3 = unorm8(byte_to_float<3>(p));
+  const float c0 = byte_to_unorm_mode<0>(p), c1 = byte_to_unorm_mode<1>(p);
+  const float c2 = byte_to_unorm_mode<2>(p), c3 = byte_to_unorm_mode<3>(p);
   if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, c3);
   return make_float4(c0, c1, c2, c3);
 }
@@ -488,14 +488,14 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
           float3 c;
           if constexpr (kStrict) c = easu_filter(sC, sF, TW, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
           else c = easu_filter_fast<TW>(sC, sF, ix, (int)fpy - sy0, ppx, ppy_full - fpy);
-          store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+          store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
         }
       } else {
         for (int k = 0; k < 8; ++k) {
           const int y = yFirst + 2 * k;
           if (y >= a.dst.h) break;
           const float3 c = easu_bilinear(sC, TW, th, tx0, sy0, x, y, a);
-          store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+          store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
         }
       }
     }
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       if (y >= a.dst.h) break;
       const float4 h = p[kRcasTW], d = p[-1], f = p[1];
       const float3 c = rcas_filter_mode(b, d, e, f, h, a.sharp);
-      store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z, 1.0f);
+      store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
       b = e; e = h; p += kRcasTW;
     }
   } else {
