@@ -3,6 +3,8 @@
 // Loading openvr_mod.cfg (jsoncpp, Win32 paths) stays with the mod; whoever owns the file fills this in.
 #pragma once
 
+#include "../../include/ovrfsr.h"
+
 struct Config {
   bool fsrEnabled = false;
   bool applyMIPBias = true; // consumed by the D3D11 sampler hook (VrHooks.cpp:94-136), not by this path
@@ -16,8 +18,7 @@ struct Config {
   int cudaDevice = -1;
   bool strictMath = false;
 
-  static Config &Instance() {
-    static Config instance;
-    return instance;
-  }
+  // ONE instance per process, owned by libovrfsr.so (an inline function-local static would be duplicated in every
+  // module that includes this header when the library is built with hidden visibility)
+  OVRFSR_API static Config &Instance();
 };

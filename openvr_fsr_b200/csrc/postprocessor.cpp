@@ -6,6 +6,11 @@
 #include <cmath>
 #include <iostream>
 
+Config &Config::Instance() {
+  static Config instance;
+  return instance;
+}
+
 static std::ostream *g_log = nullptr;
 std::ostream &Log() { return g_log ? *g_log : std::clog; }
 void SetLogStream(std::ostream *os) { g_log = os; }
