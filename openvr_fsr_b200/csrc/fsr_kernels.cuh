@@ -316,10 +316,14 @@ __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, i
   return make_float3(tR * wy0 + bR * fy, tG * wy0 + bG * fy, tB * wy0 + bB * fy);
 }
 
-// 3-channel decode of a packed RGBA8/BGRA8 texel (EASU never reads source alpha: its output alpha is 1)
+// 3-channel decode of a packed RGBA8/BGRA8 texel (EASU never reads source alpha: its output alpha is 1).
+// ALWAYS the exact decode, also in fast math: where luma is flat but chroma varies, FsrEasuSetF divides rounding
+// noise by rounding noise (|lD-lB| / max(|lD-lC|,|lC-lB|) with all three lumas equal up to the last bit), so the
+// edge strength there is defined by the exact bits of the decoded values; a decode that is 1 ulp off changes the
+// result by several LSB at such pixels.
 template <int FMT>
 __device__ __forceinline__ float4 decode_rgb1(uint32_t p) {
-  const float c0 = byte_to_unorm_mode<0>(p), c1 = byte_to_unorm_mode<1>(p), c2 = byte_to_unorm_mode<2>(p);
+  const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p)), c2 = unorm8(byte_to_float<2>(p));
   if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, 1.0f);
   return make_float4(c0, c1, c2, 1.0f);
 }
