@@ -124,17 +124,10 @@ __device__ __forceinline__ void store_texel(uint8_t *__restrict__ row, int x, fl
     reinterpret_cast<uint32_t *>(row)[x] = p;
   }
 }
-// opaque RGBA8 pixel from three floats.  Fast math rounds with the 2^23 magic add (FFMA + byte permutes, no F2I):
-// round-to-nearest-even instead of floor(x+0.5), identical except on exact .5 ties.
+// opaque RGBA8 pixel from three floats: floor(sat(v)*255 + 0.5) per channel (a 2^23 magic-add would round exact .5
+// ties to even, and bilinear taps with 1/256 weights land on exact ties about 1% of the time), two byte permutes to pack.
 __device__ __forceinline__ uint32_t pack_rgba8_opaque(float r, float g, float b) {
-  if constexpr (kStrict) {
-    return to_unorm8(r) | (to_unorm8(g) << 8) | (to_unorm8(b) << 16) | 0xff000000u;
-  } else {
-    const uint32_t rb = f2u(__fmaf_rn(__saturatef(r), 255.0f, 8388608.0f));
-    const uint32_t gb = f2u(__fmaf_rn(__saturatef(g), 255.0f, 8388608.0f));
-    const uint32_t bb = f2u(__fmaf_rn(__saturatef(b), 255.0f, 8388608.0f));
-    return __byte_perm(__byte_perm(rb, gb, 0x0040), bb, 0x0410) | 0xff000000u;
-  }
+  return __byte_perm(__byte_perm(to_unorm8(r), to_unorm8(g), 0x0040), to_unorm8(b), 0x0410) | 0xff000000u;
 }
 // store (r,g,b,1): the common case of every filter on this path
 template <int FMT>
