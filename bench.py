@@ -44,6 +44,16 @@ METRIC = "stereo eye-pairs/sec EASU+RCAS @2244x2492"
 WORKLOAD = "C2: stereo 1683x1869->2244x2492 RGBA8, renderScale=0.75, sharpness=0.9, FSR EASU+RCAS"
 
 
+def _profile_constants():
+    """Per-launch DRAM traffic and executed instructions per output pixel of the shipped kernels on this workload,
+    taken from the committed ncu captures (profiles/kernel_constants.json, written by tools/ncu_summary.py)."""
+    p = ROOT / "profiles" / "kernel_constants.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -55,18 +65,20 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons while the timed workload runs (B200_PROFILING.md recipe).  The sampler
+    is started before the warm-up (nvidia-smi needs ~100 ms to produce its first row); rows are time-stamped on
+    arrival and only those inside the marked window [mark_begin, mark_end] count."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -75,7 +87,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def samples_in_window(self):
+        return sum(1 for ts, _ in self.rows if self.t0 is not None and ts >= self.t0 and (self.t1 is None or ts <= self.t1))
 
     def stop(self):
         if self.proc is None:
@@ -85,18 +106,20 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is None or ts < self.t0 or (self.t1 is not None and ts > self.t1):
+                continue
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -223,12 +246,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.mark_begin()
     launches0 = ovr.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -237,11 +261,23 @@ def main():
     ev1.record()
     barrier()
     launches = ovr.kernel_launches() - launches0
+    clock_note = "sampled inside the timed region"
+    if rank == 0 and sampler.samples_in_window() < 5:
+        # a short timed region (tens of ms) can fall between two nvidia-smi rows: keep the SAME steps running,
+        # untimed, until a handful of rows under load exist
+        clock_note = "timed region shorter than the sampling period: sampled during identical untimed steps run right after it"
+        t_end = time.perf_counter() + 1.5
+        while sampler.samples_in_window() < 5 and time.perf_counter() < t_end:
+            step()
+            torch.cuda.synchronize()
+    sampler.mark_end()
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["note"] = clock_note
     pairs = world * args.pool * args.steps
     value = pairs / (elapsed_ms * 1e-3)
 
@@ -250,12 +286,24 @@ def main():
     peak, peak_src = _peaks()
     easu_gbs = EASU_BYTES_PER_EYE / (easu_ms * 1e-3) / 1e9
     rcas_gbs = RCAS_BYTES_PER_EYE / (rcas_ms * 1e-3) / 1e9
+    prof = _profile_constants()
+    sm_clock_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    def issue_frac(instr_per_px, ms):  # executed warp-instructions / s against 4 issue slots / SM / clock
+        if not instr_per_px:
+            return None
+        return instr_per_px * OUT_W * OUT_H / 32 / (ms * 1e-3) / (148 * 4 * sm_clock_hz * 1e6)
     roofline = {"bound": "hbm", "kernel": "easu_kernel", "achieved": easu_gbs, "peak": peak, "unit": "GB/s",
-                "frac": easu_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": easu_gbs / peak, "traffic": prof.get("easu_traffic_bytes"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": EASU_BYTES_PER_EYE, "ms_per_launch": easu_ms,
-                "note": "EASU is FP32-issue-bound, not HBM-bound, when the mask is off (DESIGN.md section 5)"}
+                "fp32_issue_frac": issue_frac(prof.get("easu_instr_per_px"), easu_ms),
+                "instr_per_output_px": prof.get("easu_instr_per_px"),
+                "note": "EASU is FP32-issue-bound, not HBM-bound, when the mask is off (DESIGN.md section 5): "
+                        "fp32_issue_frac = executed warp-instructions/s (ncu count x live launch rate) / issue peak"}
     roofline_rcas = {"bound": "hbm", "kernel": "rcas_kernel", "achieved": rcas_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": rcas_gbs / peak, "algorithmic_bytes_per_launch": RCAS_BYTES_PER_EYE, "ms_per_launch": rcas_ms}
+                     "frac": rcas_gbs / peak, "traffic": prof.get("rcas_traffic_bytes"),
+                     "algorithmic_bytes_per_launch": RCAS_BYTES_PER_EYE, "ms_per_launch": rcas_ms,
+                     "fp32_issue_frac": issue_frac(prof.get("rcas_instr_per_px"), rcas_ms),
+                     "instr_per_output_px": prof.get("rcas_instr_per_px")}
 
     # ---- end to end: host buffers through the public API, copies inside the timed region
     e2e = None
