@@ -286,7 +286,8 @@ def main():
     peak, peak_src = _peaks()
     easu_gbs = EASU_BYTES_PER_EYE / (easu_ms * 1e-3) / 1e9
     rcas_gbs = RCAS_BYTES_PER_EYE / (rcas_ms * 1e-3) / 1e9
-    prof = _profile_constants()
+    prof_all = _profile_constants()
+    prof = {k[: -len(args.math) - 1]: v for k, v in prof_all.items() if k.endswith("_" + args.math)}
     sm_clock_hz = (clocks or {}).get("sm_mhz") or 1965.0
     def issue_frac(instr_per_px, ms):  # executed warp-instructions / s against 4 issue slots / SM / clock
         if not instr_per_px:
