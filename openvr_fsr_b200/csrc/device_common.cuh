@@ -151,8 +151,17 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 typedef float2 f2;
 __device__ __forceinline__ f2 bc(float x) { return make_float2(x, x); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (it honours .rn only for scalar
+// f32), which would change results in the strict build.  There the packed multiply / add are therefore written as
+// explicit FMAs -- a*b + (-0) and a*1 + b are exact, and two FMAs cannot be contracted into one.
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  if constexpr (kStrict) return __ffma2_rn(a, b, make_float2(-0.0f, -0.0f));
+  else return __fmul2_rn(a, b);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  if constexpr (kStrict) return __ffma2_rn(a, make_float2(1.0f, 1.0f), b);
+  else return __fadd2_rn(a, b);
+}
 
 // Coordinate arithmetic is NEVER contracted, in either math mode: its result feeds floor()/int conversion, and a
 // value that lands exactly on an integer (e.g. out x=140 of a 211->281 upscale maps to source 105.0) would pick a
