@@ -152,14 +152,18 @@ typedef float2 f2;
 __device__ __forceinline__ f2 bc(float x) { return make_float2(x, x); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (it honours .rn only for scalar
-// f32), which would change results in the strict build.  There the packed multiply / add are therefore written as
-// explicit FMAs -- a*b + (-0) and a*1 + b are exact, and two FMAs cannot be contracted into one.
+// f32), and it also folds a literal "a*b + (-0)" / "a*1 + b" back into mul / add and then contracts those -- either
+// would change results in the strict build (caught by the FP32-output parity tests).  The strict packed multiply / add
+// are therefore FMAs against NEUTRAL ELEMENTS THE COMPILER CANNOT SEE: a __constant__ pair (-0, 1) that the host could
+// overwrite, so it is loaded at run time.  fma(a, b, -0) = rn(a*b) and fma(a, 1, b) = rn(a+b) exactly (including
+// the sign of zero), each a single rounding, and two real FMAs cannot be merged.
+__constant__ float g_neutral[2] = {-0.0f, 1.0f};
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-  if constexpr (kStrict) return __ffma2_rn(a, b, make_float2(-0.0f, -0.0f));
+  if constexpr (kStrict) return __ffma2_rn(a, b, bc(g_neutral[0]));
   else return __fmul2_rn(a, b);
 }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  if constexpr (kStrict) return __ffma2_rn(a, make_float2(1.0f, 1.0f), b);
+  if constexpr (kStrict) return __ffma2_rn(a, bc(g_neutral[1]), b);
   else return __fadd2_rn(a, b);
 }
 

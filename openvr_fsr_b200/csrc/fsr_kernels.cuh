@@ -68,34 +68,34 @@ __device__ __forceinline__ float4 easu_feature(float lA, float lB, float lC, flo
   return make_float4(dirX, dirY, lenX, lenY);
 }
 
-// ---- strict math: FsrEasuF in the reference's operation order, two lanes at a time --------------------------
-// FMUL2 / FADD2 are IEEE per lane and are never contracted in the strict build (-fmad=false), so packing two
-// INDEPENDENT scalar chains side by side changes no bit: (dirX,dirY), (r,g), (b,weight) and two horizontally
-// adjacent taps share an instruction.  Every lane still performs exactly the reference's sequence
-//   FsrEasuSetF :275-313   dir += d*w ; len += lenX*w ; len += lenY*w          (corners f,g,j,k in that order)
-//   FsrEasuTapF :239-272   v=(o.x*d.x)+(o.y*d.y), (o.x*-d.y)+(o.y*d.x); v*=len; d2=v.x*v.x+v.y*v.y; min; wB; wA; ...
-//   accumulate  :423-434   taps in the order b c i j f e k l h g o n
-// Products that the reference recomputes per tap (o.x*d.x for the 4 distinct o.x, o.y*d.y for the 4 distinct o.y)
-// are formed once: the same operands give the same product.
-__device__ __forceinline__ f2 easu_w2_strict(f2 X, f2 N, float yd, float yx, float len0, float len1, float lob, float clp) {
-  f2 vx = add2(X, bc(yd)), vy = add2(N, bc(yx));
-  vx = mul2(vx, bc(len0));
-  vy = mul2(vy, bc(len1));
-  f2 d2 = add2(mul2(vx, vx), mul2(vy, vy));
-  d2.x = fminf(d2.x, clp);
-  d2.y = fminf(d2.y, clp);
-  f2 wB = add2(mul2(bc((float)(2.0 / 5.0)), d2), bc((float)(-1.0)));
-  f2 wA = add2(mul2(bc(lob), d2), bc((float)(-1.0)));
-  wB = mul2(wB, wB);
-  wA = mul2(wA, wA);
-  wB = add2(mul2(bc((float)(25.0 / 16.0)), wB), bc((float)(-(25.0 / 16.0 - 1.0))));
-  return mul2(wB, wA);
-}
-__device__ __forceinline__ void easu_acc_strict(f2 &aRG, f2 &aBW, const float4 c, float w) {
-  aRG = add2(aRG, mul2(make_float2(c.x, c.y), bc(w)));
-  aBW = add2(aBW, mul2(make_float2(c.z, c.w), bc(w))); // c.w == 1: 1*w == w exactly, so this lane is aW += w
+// ---- strict math: FsrEasuF in the reference's operation order (scalar) ----------------------------------------
+// (A two-lane FMUL2/FADD2 version exists in the history: it is bit-exact too -- with the neutral-element trick of
+// device_common.cuh against ptxas' f32x2 contraction -- but every strict mul and add is its own FMA-pipe op either
+// way, so it was FMA-pipe-bound and 3 % slower than this scalar form.)
+// Products the reference recomputes per tap are formed once: off.x*dir.x and off.x*(-dir.y) for the 4 distinct
+// off.x, off.y*dir.y and off.y*dir.x for the 4 distinct off.y -- same operands, same product, 16 multiplies
+// instead of 48.
+// FsrEasuTapF, ffx_fsr1.h:239-272, from the two products of each coordinate
+__device__ __forceinline__ void easu_tap_ref(float &aR, float &aG, float &aB, float &aW, float xdx, float ydy, float xndy,
+                                             float ydx, float len0, float len1, float lob, float clp, const float4 c) {
+  float vx = xdx + ydy;   // (off.x*dir.x) + (off.y*dir.y)
+  float vy = xndy + ydx;  // (off.x*(-dir.y)) + (off.y*dir.x)
+  vx *= len0;
+  vy *= len1;
+  float d2 = vx * vx + vy * vy;
+  d2 = fminf(d2, clp);
+  float wB = (float)(2.0 / 5.0) * d2 + (float)(-1.0);
+  float wA = lob * d2 + (float)(-1.0);
+  wB *= wB;
+  wA *= wA;
+  wB = (float)(25.0 / 16.0) * wB + (float)(-(25.0 / 16.0 - 1.0));
+  const float w = wB * wA;
+  aR += c.x * w; aG += c.y * w; aB += c.z * w;
+  aW += w;
 }
 
+// FsrEasuF, ffx_fsr1.h:315-437, for the output pixel whose 'f' texel sits at tile coords (ix,iy)
+// with sub-texel phase (ppx,ppy).  sC = decoded colours (xyz), sF = per-texel features.
 template <int TW>
 __device__ __forceinline__ float3 easu_filter(const float4 *__restrict__ sC, const float4 *__restrict__ sF, int ix, int iy,
                                               float ppx, float ppy) {
@@ -103,80 +103,67 @@ __device__ __forceinline__ float3 easu_filter(const float4 *__restrict__ sC, con
   const float4 *fr = sF + iy * TW + ix;
   const float4 Ff = fr[0], Fg = fr[1], Fj = fr[TW], Fk = fr[TW + 1];
   const float qx = 1.0f - ppx, qy = 1.0f - ppy;
-  const f2 wt = mul2(make_float2(qx, ppx), bc(qy)), wb = mul2(make_float2(qx, ppx), bc(ppy)); // (wf,wg) (wj,wk)
-  f2 dir = bc(0.0f);
-  float len = 0.0f;
-  {
-    f2 p;
-    dir = add2(dir, mul2(make_float2(Ff.x, Ff.y), bc(wt.x))); p = mul2(make_float2(Ff.z, Ff.w), bc(wt.x)); len += p.x; len += p.y;
-    dir = add2(dir, mul2(make_float2(Fg.x, Fg.y), bc(wt.y))); p = mul2(make_float2(Fg.z, Fg.w), bc(wt.y)); len += p.x; len += p.y;
-    dir = add2(dir, mul2(make_float2(Fj.x, Fj.y), bc(wb.x))); p = mul2(make_float2(Fj.z, Fj.w), bc(wb.x)); len += p.x; len += p.y;
-    dir = add2(dir, mul2(make_float2(Fk.x, Fk.y), bc(wb.y))); p = mul2(make_float2(Fk.z, Fk.w), bc(wb.y)); len += p.x; len += p.y;
-  }
+  const float wf = qx * qy, wg = ppx * qy, wj = qx * ppy, wk = ppx * ppy;
+  float dirX = 0.0f, dirY = 0.0f, len = 0.0f;
+  dirX += Ff.x * wf; len += Ff.z * wf; dirY += Ff.y * wf; len += Ff.w * wf;
+  dirX += Fg.x * wg; len += Fg.z * wg; dirY += Fg.y * wg; len += Fg.w * wg;
+  dirX += Fj.x * wj; len += Fj.z * wj; dirY += Fj.y * wj; len += Fj.w * wj;
+  dirX += Fk.x * wk; len += Fk.z * wk; dirY += Fk.y * wk; len += Fk.w * wk;
+
   // normalise (:389-395)
-  f2 dd = mul2(dir, dir);
-  float dirR = dd.x + dd.y;
+  const float dir2x = dirX * dirX, dir2y = dirY * dirY;
+  float dirR = dir2x + dir2y;
   const bool zro = dirR < (float)(1.0 / 32768.0);
   dirR = prx_lo_rsq(dirR);
   dirR = zro ? 1.0f : dirR;
-  dir.x = zro ? 1.0f : dir.x;
-  dir = mul2(dir, bc(dirR));
+  dirX = zro ? 1.0f : dirX;
+  dirX *= dirR;
+  dirY *= dirR;
   // shape (:397-409)
   len = len * 0.5f;
   len *= len;
-  dd = mul2(dir, dir);
-  const float stretch = (dd.x + dd.y) * prx_lo_rcp(fmaxf(fabsf(dir.x), fabsf(dir.y)));
+  const float stretch = (dirX * dirX + dirY * dirY) * prx_lo_rcp(fmaxf(fabsf(dirX), fabsf(dirY)));
   const float len0 = 1.0f + (stretch - 1.0f) * len;
   const float len1 = 1.0f + (-0.5f) * len;
   const float lob = 0.5f + (float)((1.0 / 4.0 - 0.04) - 0.5) * len;
   const float clp = prx_lo_rcp(lob);
 
-  // tap offsets o - pp: x pairs (-1,0) (0,1) (1,2); y scalars -1,0,1,2
-  const f2 mpx = bc(-ppx), mpy = bc(-ppy);
-  const f2 oxA = add2(make_float2(-1.0f, 0.0f), mpx), oxB = add2(make_float2(0.0f, 1.0f), mpx),
-           oxC = add2(make_float2(1.0f, 2.0f), mpx);
-  const f2 oyA = add2(make_float2(-1.0f, 0.0f), mpy), oyB = add2(make_float2(1.0f, 2.0f), mpy);
-  const f2 dx = bc(dir.x), ndy = bc(-dir.y);
-  const f2 XA = mul2(oxA, dx), XB = mul2(oxB, dx), XC = mul2(oxC, dx);    // off.x * dir.x
-  const f2 NA = mul2(oxA, ndy), NB = mul2(oxB, ndy), NC = mul2(oxC, ndy); // off.x * (-dir.y)
-  const f2 ydA = mul2(oyA, bc(dir.y)), ydB = mul2(oyB, bc(dir.y));        // off.y * dir.y  for rows -1,0 / 1,2
-  const f2 yxA = mul2(oyA, dx), yxB = mul2(oyB, dx);                      // off.y * dir.x
+  // the 4 distinct off.x / off.y values and their products with dir (shared by the 12 taps)
+  const float ndirY = -dirY;
+  const float ox0 = -1.0f - ppx, ox1 = 0.0f - ppx, ox2 = 1.0f - ppx, ox3 = 2.0f - ppx;
+  const float oy0 = -1.0f - ppy, oy1 = 0.0f - ppy, oy2 = 1.0f - ppy, oy3 = 2.0f - ppy;
+  const float xd0 = ox0 * dirX, xd1 = ox1 * dirX, xd2 = ox2 * dirX, xd3 = ox3 * dirX;
+  const float xn0 = ox0 * ndirY, xn1 = ox1 * ndirY, xn2 = ox2 * ndirY, xn3 = ox3 * ndirY;
+  const float yd0 = oy0 * dirY, yd1 = oy1 * dirY, yd2 = oy2 * dirY, yd3 = oy3 * dirY;
+  const float yx0 = oy0 * dirX, yx1 = oy1 * dirX, yx2 = oy2 * dirX, yx3 = oy3 * dirX;
 
   //    b c
   //  e f g h
   //  i j k l
   //    n o
-  const f2 wbc = easu_w2_strict(XB, NB, ydA.x, yxA.x, len0, len1, lob, clp);
-  const f2 wef = easu_w2_strict(XA, NA, ydA.y, yxA.y, len0, len1, lob, clp);
-  const f2 wgh = easu_w2_strict(XC, NC, ydA.y, yxA.y, len0, len1, lob, clp);
-  const f2 wij = easu_w2_strict(XA, NA, ydB.x, yxB.x, len0, len1, lob, clp);
-  const f2 wkl = easu_w2_strict(XC, NC, ydB.x, yxB.x, len0, len1, lob, clp);
-  const f2 wno = easu_w2_strict(XB, NB, ydB.y, yxB.y, len0, len1, lob, clp);
-
   const float4 *r0 = sC + (iy - 1) * TW + ix;
   const float4 f = r0[TW], g = r0[TW + 1], j = r0[2 * TW], k = r0[2 * TW + 1];
-  f2 aRG = bc(0.0f), aBW = bc(0.0f);
-  // reference accumulation order (:423-434): b c i j f e k l h g o n
-  easu_acc_strict(aRG, aBW, r0[0], wbc.x);
-  easu_acc_strict(aRG, aBW, r0[1], wbc.y);
-  easu_acc_strict(aRG, aBW, r0[2 * TW - 1], wij.x);
-  easu_acc_strict(aRG, aBW, j, wij.y);
-  easu_acc_strict(aRG, aBW, f, wef.y);
-  easu_acc_strict(aRG, aBW, r0[TW - 1], wef.x);
-  easu_acc_strict(aRG, aBW, k, wkl.x);
-  easu_acc_strict(aRG, aBW, r0[2 * TW + 2], wkl.y);
-  easu_acc_strict(aRG, aBW, r0[TW + 2], wgh.y);
-  easu_acc_strict(aRG, aBW, g, wgh.x);
-  easu_acc_strict(aRG, aBW, r0[3 * TW + 1], wno.y);
-  easu_acc_strict(aRG, aBW, r0[3 * TW], wno.x);
+  float aR = 0.0f, aG = 0.0f, aB = 0.0f, aW = 0.0f;
+  // reference accumulation order (:423-434): b c i j f e k l h g o n   (index 0..3 <-> offset -1..2)
+  easu_tap_ref(aR, aG, aB, aW, xd1, yd0, xn1, yx0, len0, len1, lob, clp, r0[0]);          // b ( 0,-1)
+  easu_tap_ref(aR, aG, aB, aW, xd2, yd0, xn2, yx0, len0, len1, lob, clp, r0[1]);          // c ( 1,-1)
+  easu_tap_ref(aR, aG, aB, aW, xd0, yd2, xn0, yx2, len0, len1, lob, clp, r0[2 * TW - 1]); // i (-1, 1)
+  easu_tap_ref(aR, aG, aB, aW, xd1, yd2, xn1, yx2, len0, len1, lob, clp, j);              // j ( 0, 1)
+  easu_tap_ref(aR, aG, aB, aW, xd1, yd1, xn1, yx1, len0, len1, lob, clp, f);              // f ( 0, 0)
+  easu_tap_ref(aR, aG, aB, aW, xd0, yd1, xn0, yx1, len0, len1, lob, clp, r0[TW - 1]);     // e (-1, 0)
+  easu_tap_ref(aR, aG, aB, aW, xd2, yd2, xn2, yx2, len0, len1, lob, clp, k);              // k ( 1, 1)
+  easu_tap_ref(aR, aG, aB, aW, xd3, yd2, xn3, yx2, len0, len1, lob, clp, r0[2 * TW + 2]); // l ( 2, 1)
+  easu_tap_ref(aR, aG, aB, aW, xd3, yd1, xn3, yx1, len0, len1, lob, clp, r0[TW + 2]);     // h ( 2, 0)
+  easu_tap_ref(aR, aG, aB, aW, xd2, yd1, xn2, yx1, len0, len1, lob, clp, g);              // g ( 1, 0)
+  easu_tap_ref(aR, aG, aB, aW, xd2, yd3, xn2, yx3, len0, len1, lob, clp, r0[3 * TW + 1]); // o ( 1, 2)
+  easu_tap_ref(aR, aG, aB, aW, xd1, yd3, xn1, yx3, len0, len1, lob, clp, r0[3 * TW]);     // n ( 0, 2)
 
   // min/max of the four nearest (:416-419), normalise and de-ring (:437)
   const float mnR = fminf(fminf(f.x, fminf(g.x, j.x)), k.x), mxR = fmaxf(fmaxf(f.x, fmaxf(g.x, j.x)), k.x);
   const float mnG = fminf(fminf(f.y, fminf(g.y, j.y)), k.y), mxG = fmaxf(fmaxf(f.y, fmaxf(g.y, j.y)), k.y);
   const float mnB = fminf(fminf(f.z, fminf(g.z, j.z)), k.z), mxB = fmaxf(fmaxf(f.z, fmaxf(g.z, j.z)), k.z);
-  const float r = rcp_mode(aBW.y);
-  const f2 pRG = mul2(aRG, bc(r));
-  return make_float3(fminf(mxR, fmaxf(mnR, pRG.x)), fminf(mxG, fmaxf(mnG, pRG.y)), fminf(mxB, fmaxf(mnB, aBW.x * r)));
+  const float r = rcp_mode(aW);
+  return make_float3(fminf(mxR, fmaxf(mnR, aR * r)), fminf(mxG, fmaxf(mnG, aG * r)), fminf(mxB, fmaxf(mnB, aB * r)));
 }
 
 // ---- fast math: FsrEasuF regrouped for the FP32x2 pipe ----------------------------------------------------
