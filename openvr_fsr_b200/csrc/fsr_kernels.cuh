@@ -270,19 +270,24 @@ __device__ __forceinline__ float3 easu_filter_fast(const float4 *__restrict__ sC
 }
 
 // Bilinear(), fsr_easu.hlsl:33-36: SampleLevel(linearClamp, float2(pos)/Radius.zw) -- no half-texel
-// offset; coordinates snapped to 1/256 texel like D3D11's fixed-point sampler.  Reads the same clamped colour tile.
-__device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, int tw, int th, int sx0, int sy0, int x,
-                                                int y, const EasuArgs &a) {
-  const float u = (float)x / a.radW, v = (float)y / a.radH;
-  const float sx = snap_subtexel(mul_add_unfused(u, (float)a.src.w, -0.5f));
-  const float sy = snap_subtexel(mul_add_unfused(v, (float)a.src.h, -0.5f));
-  const float fx0 = floorf(sx), fy0 = floorf(sy);
-  const float fx = sx - fx0, fy = sy - fy0;
-  const int tx0 = clampi((int)fx0 - sx0, 0, tw - 1), tx1 = clampi((int)fx0 + 1 - sx0, 0, tw - 1);
-  const int ty0 = clampi((int)fy0 - sy0, 0, th - 1), ty1 = clampi((int)fy0 + 1 - sy0, 0, th - 1);
-  const float4 c00 = sC[ty0 * tw + tx0], c10 = sC[ty0 * tw + tx1];
-  const float4 c01 = sC[ty1 * tw + tx0], c11 = sC[ty1 * tw + tx1];
-  const float wx0 = 1.0f - fx, wy0 = 1.0f - fy;
+// offset; coordinates snapped to 1/256 texel like D3D11's fixed-point sampler.  The sample position is separable:
+// the x part (one IEEE divide, snap, floor) depends only on the output column and the y part only on the output row,
+// so each is evaluated once per column / row instead of once per pixel -- same operations, same bits.
+struct BilinAxis { int t0, t1; float f; }; // clamped tile coordinates of the two taps and the weight of the second
+__device__ __forceinline__ BilinAxis easu_bilinear_axis(int p, float rad, int srcExtent, int tileOrigin, int tileExtent) {
+  const float u = (float)p / rad;
+  const float s = snap_subtexel(mul_add_unfused(u, (float)srcExtent, -0.5f));
+  const float s0 = floorf(s);
+  BilinAxis r;
+  r.f = s - s0;
+  r.t0 = clampi((int)s0 - tileOrigin, 0, tileExtent - 1);
+  r.t1 = clampi((int)s0 + 1 - tileOrigin, 0, tileExtent - 1);
+  return r;
+}
+__device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, int tw, const BilinAxis ax, const BilinAxis ay) {
+  const float4 c00 = sC[ay.t0 * tw + ax.t0], c10 = sC[ay.t0 * tw + ax.t1];
+  const float4 c01 = sC[ay.t1 * tw + ax.t0], c11 = sC[ay.t1 * tw + ax.t1];
+  const float fx = ax.f, fy = ay.f, wx0 = 1.0f - fx, wy0 = 1.0f - fy;
   const float tR = c00.x * wx0 + c10.x * fx, bR = c01.x * wx0 + c11.x * fx;
   const float tG = c00.y * wx0 + c10.y * fx, bG = c01.y * wx0 + c11.y * fx;
   const float tB = c00.z * wx0 + c10.z * fx, bB = c01.z * wx0 + c11.z * fx;
@@ -322,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap srcMap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint64_t tileBar;
+  __shared__ BilinAxis sRowAxis[kTileH]; // Bilinear()'s row terms of this tile (outside-radius groups only)
   const int th = a.tileH, tn = TW * th;
   float4 *sC = reinterpret_cast<float4 *>(smem_raw);  // decoded colour (r,g,b,1)
   float4 *sF = sC + tn;                               // (dirX, dirY, lenX, lenY) per texel
@@ -408,6 +414,8 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
         }
       }
     }
+    // one row term per output row of the tile for the bilinear fallback (skipped when every group is inside)
+    if (tid < kTileH && oy0 + tid < a.dst.h) sRowAxis[tid] = easu_bilinear_axis(oy0 + tid, a.radH, a.src.h, sy0, th);
     const int anyInside = __syncthreads_or(inside);
     if constexpr (TMA) {
       // the landing zone is fully decoded: refill it with the NEXT tile's box while this tile is filtered
@@ -468,10 +476,12 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
           store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
         }
       } else {
+        const BilinAxis ax = easu_bilinear_axis(x, a.radW, a.src.w, tx0, cols);
+#pragma unroll 2
         for (int k = 0; k < 8; ++k) {
           const int y = yFirst + 2 * k;
           if (y >= a.dst.h) break;
-          const float3 c = easu_bilinear(sC, TW, th, tx0, sy0, x, y, a);
+          const float3 c = easu_bilinear(sC, TW, ax, sRowAxis[y - oy0]);
           store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
         }
       }
@@ -562,10 +572,13 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
   const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
 
   if constexpr (TMA) {
-    __syncthreads();
+    // a CTA whose 8 groups are all outside the radius and copy raw bytes needs no decoded tile at all
+    const bool rawCopy = FIN == OVRFSR_FORMAT_RGBA8 && FOUT == OVRFSR_FORMAT_RGBA8 && a.tintGB == 1.0f;
+    const int needTile = __syncthreads_or(inside || !rawCopy); // also orders the barrier init before the polls
     mbar_wait(&tileBar, 0);
-    for (int ty = warp; ty < kRcasTH; ty += kThreads / 32)
-      for (int tx = lane; tx < kTileW + 2; tx += 32) sC[ty * kRcasTW + tx] = decode_rgba<FIN>(sRaw[ty * kRcasRawW + tx + 3]);
+    if (needTile)
+      for (int ty = warp; ty < kRcasTH; ty += kThreads / 32)
+        for (int tx = lane; tx < kTileW + 2; tx += 32) sC[ty * kRcasTW + tx] = decode_rgba<FIN>(sRaw[ty * kRcasRawW + tx + 3]);
   } else {
     // Texture2D.Load semantics: out of bounds reads 0 (fsr_rcas.hlsl:18)
     for (int ty = warp; ty < kRcasTH; ty += kThreads / 32) {
@@ -599,6 +612,20 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
     }
   } else {
     // OutputTexture[p] = mul * InputTexture[p], alpha included (fsr_rcas.hlsl:45-53)
+    if constexpr (TMA && FIN == OVRFSR_FORMAT_RGBA8 && FOUT == OVRFSR_FORMAT_RGBA8) {
+      if (a.tintGB == 1.0f) {
+        // debug tint off: mul == 1 and decode -> x1 -> encode is the identity on all 256 codes (exhaustive check in
+        // tests/test_host_logic.py), so the texel bytes are copied straight from the TMA landing zone
+        const uint32_t *q = sRaw + (y0 - sy0) * kRcasRawW + (x - sx0) + 3;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int y = y0 + k;
+          if (y >= a.dst.h) break;
+          reinterpret_cast<uint32_t *>(a.dst.ptr + (size_t)y * a.dst.pitch)[x] = q[k * kRcasRawW];
+        }
+        return;
+      }
+    }
     for (int k = 0; k < 8; ++k) {
       const int y = y0 + k;
       if (y >= a.dst.h) break;
