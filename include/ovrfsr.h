@@ -170,6 +170,10 @@ OVRFSR_API const float *ovrfsr_nis_coef_usm(void);
 /* constant blocks the ctx built for `eye` (valid after the first apply) */
 OVRFSR_API int ovrfsr_get_upscale_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts[24]);
 OVRFSR_API int ovrfsr_get_sharpen_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts[12]);
+/* Device self-test: strict-math RCAS replaces rcp.rn by MUFU.RCP + one Newton step when the source is UNORM8 (its
+ * reciprocal operands then come from a set of 512 values); this runs both over the whole set on the current device.
+ * *mismatches must come back 0. */
+OVRFSR_API int ovrfsr_selftest_rcp(uint32_t *mismatches, uint32_t *checked);
 /* kernels launched by this library in this process since load (bench.py's gpu_launches) */
 OVRFSR_API uint64_t ovrfsr_kernel_launches(void);
 /* debugMode profiling (PostProcessor.cpp:547-557,601-628): mean GPU ms per apply over the samples

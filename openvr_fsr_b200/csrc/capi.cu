@@ -417,6 +417,13 @@ int ovrfsr_get_sharpen_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts
   std::memcpy(consts, ctx->sharpenConstants[ctx->textureContainsOnlyOneEye ? eye : 0], 48);
   return OVRFSR_OK;
 }
+int ovrfsr_selftest_rcp(uint32_t *mismatches, uint32_t *checked) {
+  uint32_t r[2] = {0, 0};
+  if (selftest_rcas_rcp(r, nullptr) != cudaSuccess) return OVRFSR_ERR_CUDA;
+  if (mismatches) *mismatches = r[0];
+  if (checked) *checked = r[1];
+  return OVRFSR_OK;
+}
 uint64_t ovrfsr_kernel_launches(void) { return ovrfsr::g_launches.load(std::memory_order_relaxed); }
 
 int ovrfsr_get_gpu_time_ms(ovrfsr_ctx *ctx, float *mean_ms) {

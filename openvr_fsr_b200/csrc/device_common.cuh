@@ -54,6 +54,23 @@ __device__ __forceinline__ float rcp_mode(float a) {
   }
 }
 
+// Strict-math reciprocal for RCAS when the source is UNORM8: the operands are 4*mx and 4*mn-4 with mx, mn in
+// {k/255}, i.e. one of 512 known values (or +0), all normal and far from overflow.  For those, MUFU.RCP plus one FMA
+// Newton step IS the correctly rounded 1/x -- checked exhaustively on the device against rcp.rn by
+// ovrfsr_selftest_rcp (tests/test_gpu_fsr_parity.py) -- without __frcp_rn's range checks and slow-path branch.
+__device__ __forceinline__ float rcp_rn_unorm8_operand(float a) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(a));
+  const float e = __fmaf_rn(-a, r0, 1.0f);
+  const float r = __fmaf_rn(r0, e, r0);
+  return a == 0.0f ? r0 : r; // 1/+0 = +inf (r would be NaN); -0 cannot occur here
+}
+template <bool UNORM8_OPERANDS>
+__device__ __forceinline__ float rcp_mode_rcas(float a) {
+  if constexpr (kStrict && UNORM8_OPERANDS) return rcp_rn_unorm8_operand(a);
+  else return rcp_mode(a);
+}
+
 // byte k of a packed texel -> exact float(v): PRMT builds 0x4B0000vv (= 2^23 + v), one FADD removes 2^23.
 template <int K>
 __device__ __forceinline__ float byte_to_float(uint32_t p) {

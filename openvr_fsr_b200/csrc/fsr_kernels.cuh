@@ -498,18 +498,19 @@ constexpr int kRcasTH = kTileH + 2;
 constexpr int kRcasRawW = kTileW + 8; // TMA box: starts 4 texels left of the tile (16-byte aligned origin), 1 used right
 
 // FsrRcasF, ffx_fsr1.h:684-769 (FSR_RCAS_DENOISE / PASSTHROUGH_ALPHA undefined: fsr_rcas.hlsl:1-4), reference order
+template <bool U8>
 __device__ __forceinline__ float3 rcas_filter(const float4 b, const float4 d, const float4 e, const float4 f,
                                               const float4 h, float sharp) {
   const float mn4R = fminf(fminf(b.x, fminf(d.x, f.x)), h.x), mx4R = fmaxf(fmaxf(b.x, fmaxf(d.x, f.x)), h.x);
   const float mn4G = fminf(fminf(b.y, fminf(d.y, f.y)), h.y), mx4G = fmaxf(fmaxf(b.y, fmaxf(d.y, f.y)), h.y);
   const float mn4B = fminf(fminf(b.z, fminf(d.z, f.z)), h.z), mx4B = fmaxf(fmaxf(b.z, fmaxf(d.z, f.z)), h.z);
   // limiters need full-precision reciprocals (:748-755)
-  const float hitMinR = mn4R * rcp_mode(4.0f * mx4R);
-  const float hitMinG = mn4G * rcp_mode(4.0f * mx4G);
-  const float hitMinB = mn4B * rcp_mode(4.0f * mx4B);
-  const float hitMaxR = (1.0f - mx4R) * rcp_mode(4.0f * mn4R + (-4.0f));
-  const float hitMaxG = (1.0f - mx4G) * rcp_mode(4.0f * mn4G + (-4.0f));
-  const float hitMaxB = (1.0f - mx4B) * rcp_mode(4.0f * mn4B + (-4.0f));
+  const float hitMinR = mn4R * rcp_mode_rcas<U8>(4.0f * mx4R);
+  const float hitMinG = mn4G * rcp_mode_rcas<U8>(4.0f * mx4G);
+  const float hitMinB = mn4B * rcp_mode_rcas<U8>(4.0f * mx4B);
+  const float hitMaxR = (1.0f - mx4R) * rcp_mode_rcas<U8>(4.0f * mn4R + (-4.0f));
+  const float hitMaxG = (1.0f - mx4G) * rcp_mode_rcas<U8>(4.0f * mn4G + (-4.0f));
+  const float hitMaxB = (1.0f - mx4B) * rcp_mode_rcas<U8>(4.0f * mn4B + (-4.0f));
   const float lobeR = fmaxf(-hitMinR, hitMaxR), lobeG = fmaxf(-hitMinG, hitMaxG), lobeB = fmaxf(-hitMinB, hitMaxB);
   const float lobe =
       fmaxf((float)(-(0.25 - (1.0 / 16.0))), fminf(fmaxf(lobeR, fmaxf(lobeG, lobeB)), 0.0f)) * sharp;
@@ -541,9 +542,10 @@ __device__ __forceinline__ float3 rcas_filter_fast(const float4 b, const float4 
   return make_float3(pRG.x, pRG.y, fmaf(lobe, sB, e.z) * rcpL);
 }
 
+template <bool U8>
 __device__ __forceinline__ float3 rcas_filter_mode(const float4 b, const float4 d, const float4 e, const float4 f,
                                                    const float4 h, float sharp) {
-  if constexpr (kStrict) return rcas_filter(b, d, e, f, h, sharp);
+  if constexpr (kStrict) return rcas_filter<U8>(b, d, e, f, h, sharp);
   else return rcas_filter_fast(b, d, e, f, h, sharp);
 }
 
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       const int y = y0 + k;
       if (y >= a.dst.h) break;
       const float4 h = p[kRcasTW], d = p[-1], f = p[1];
-      const float3 c = rcas_filter_mode(b, d, e, f, h, a.sharp);
+      const float3 c = rcas_filter_mode<FIN == OVRFSR_FORMAT_RGBA8 || FIN == OVRFSR_FORMAT_BGRA8>(b, d, e, f, h, a.sharp);
       store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
       b = e; e = h; p += kRcasTW;
     }
@@ -633,6 +635,19 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       store_texel<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, 1.0f * e.x, a.tintGB * e.y, a.tintGB * e.z, 1.0f * e.w);
     }
   }
+}
+
+// Device self-test behind ovrfsr_selftest_rcp: every reciprocal operand strict RCAS can see with a UNORM8 source,
+// fast sequence vs rcp.rn.  out[0] = number of mismatching operands (must be 0), out[1] = operands checked.
+__global__ void rcas_rcp_selftest_kernel(uint32_t *out) {
+  const int k = threadIdx.x; // 0..255
+  const float v = unorm8((float)k);
+  const float x1 = 4.0f * v, x2 = __fadd_rn(__fmul_rn(4.0f, v), -4.0f);
+  int bad = 0;
+  bad += f2u(rcp_rn_unorm8_operand(x1)) != f2u(__frcp_rn(x1));
+  bad += f2u(rcp_rn_unorm8_operand(x2)) != f2u(__frcp_rn(x2));
+  atomicAdd(&out[0], (uint32_t)bad);
+  atomicAdd(&out[1], 2u);
 }
 
 } // inline namespace OVRFSR_MODE_NS

@@ -22,6 +22,9 @@ cudaError_t launch_nis_scaler_strict(const PassImage &src, const PassImage &dst,
 cudaError_t launch_nis_sharpen_fast(const PassImage &src, const PassImage &dst, const void *cfg256, const float *coef, cudaStream_t s);
 cudaError_t launch_nis_sharpen_strict(const PassImage &src, const PassImage &dst, const void *cfg256, const float *coef, cudaStream_t s);
 
+// exhaustive device check of strict RCAS's UNORM8 reciprocal: result = {mismatches, operands checked}
+cudaError_t selftest_rcas_rcp(uint32_t result[2], cudaStream_t s);
+
 // bumped once per kernel launch by every launcher (ovrfsr_kernel_launches)
 void count_launch();
 

@@ -141,3 +141,13 @@ def test_tma_and_plain_loaders_agree(cuda, iw, ih, scale):
             assert np.array_equal(outs[(ovr.MATH_STRICT, name)][0], easu) and np.array_equal(outs[(ovr.MATH_STRICT, name)][1], rcas)
         assert np.array_equal(outs[(ovr.MATH_FAST, "tight")][0], outs[(ovr.MATH_FAST, "pitched")][0])
         assert np.array_equal(outs[(ovr.MATH_FAST, "tight")][1], outs[(ovr.MATH_FAST, "pitched")][1])
+
+
+def test_strict_rcas_reciprocal_is_exact_on_every_unorm8_operand(cuda):
+    """Strict RCAS uses MUFU.RCP + one Newton step instead of rcp.rn for UNORM8 sources; exhaustive device check over
+    all 512 operands (4*k/255 and 4*k/255-4) that it equals rcp.rn bit for bit."""
+    import ctypes as C
+    from openvr_fsr_b200 import _lib as L
+    bad, n = C.c_uint32(99), C.c_uint32(0)
+    L.check(L.lib().ovrfsr_selftest_rcp(C.byref(bad), C.byref(n)))
+    assert n.value == 512 and bad.value == 0
