@@ -1,7 +1,7 @@
 import sys
 from pathlib import Path
 import numpy as np, torch
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import openvr_fsr_b200 as ovr
 from openvr_fsr_b200 import synth
 from oracle import pyoracle as po
