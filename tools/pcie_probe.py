@@ -1,0 +1,22 @@
+"""Dev probe: H2D / D2H bandwidth of eye-sized images, contiguous vs pitched (2-D) copies, one and two directions."""
+import time, torch
+dev = torch.device("cuda:0")
+def bw(fn, nbytes, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); t = time.perf_counter()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize(); return nbytes * reps / (time.perf_counter() - t) / 1e9
+H, W = 2492, 2244 * 4
+hp = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+dc = torch.empty((H, W), dtype=torch.uint8, device=dev)
+dp = torch.empty((H, 9216), dtype=torch.uint8, device=dev)[:, :W]
+print("D2H contiguous GB/s", bw(lambda: hp.copy_(dc, non_blocking=True), H * W))
+print("D2H pitched    GB/s", bw(lambda: hp.copy_(dp, non_blocking=True), H * W))
+print("H2D contiguous GB/s", bw(lambda: dc.copy_(hp, non_blocking=True), H * W))
+print("H2D pitched    GB/s", bw(lambda: dp.copy_(hp, non_blocking=True), H * W))
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+hp2 = torch.empty((H, W), dtype=torch.uint8).pin_memory(); dc2 = torch.empty((H, W), dtype=torch.uint8, device=dev)
+def both():
+    with torch.cuda.stream(s1): dc.copy_(hp, non_blocking=True)
+    with torch.cuda.stream(s2): hp2.copy_(dc2, non_blocking=True)
+print("bidirectional contiguous GB/s (sum)", bw(both, 2 * H * W))
