@@ -406,19 +406,20 @@ def quick_value(ovr, torch, cfg, pool, steps, **changes):
 
 def e2e_run(ovr, torch, dist, cfg, pool, dev, world, steps, warmup):
     """Same metric through the reference-facing call with HOST buffers: per eye, pinned host -> device copy,
-    EASU+RCAS, device -> pinned host copy, all inside the timed region.  Two streams (one per eye) so the two
-    copy engines and the SMs overlap."""
-    pp = ovr.PostProcessor(cfg)
+    EASU+RCAS, device -> pinned host copy, all inside the timed region.  Two PostProcessor contexts are ping-ponged
+    (frame i uses context i % 2, each with one stream per eye) so that the upload of frame i+1 overlaps the download
+    of frame i: a context owns its staging / output images, so frames in flight need one context each."""
+    pps = [ovr.PostProcessor(cfg), ovr.PostProcessor(cfg)]
     n = len(pool)
     h_in = [(l.cpu().contiguous().pin_memory(), r.cpu().contiguous().pin_memory()) for l, r in pool]
     h_out = [(torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8).pin_memory(),
               torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8).pin_memory()) for _ in range(n)]
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    streams = [[torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] for _ in pps]
 
     def step():
         for i in range(n):
             for eye in (0, 1):
-                pp.apply_host(eye, h_in[i][eye], h_out[i][eye], stream=streams[eye])
+                pps[i & 1].apply_host(eye, h_in[i][eye], h_out[i][eye], stream=streams[i & 1][eye])
 
     for _ in range(max(1, min(warmup, 2))):
         step()
@@ -427,22 +428,24 @@ def e2e_run(ovr, torch, dist, cfg, pool, dev, world, steps, warmup):
         dist.barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(streams[0])
+    e0.record(streams[0][0])
     for _ in range(steps):
         step()
-    streams[0].wait_stream(streams[1])
-    e1.record(streams[0])
+    for s in (streams[0][1], streams[1][0], streams[1][1]):
+        streams[0][0].wait_stream(s)
+    e1.record(streams[0][0])
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    pp.close()
+    for p in pps:
+        p.close()
     pairs = world * n * steps
     return {"value": pairs / (float(ms.item()) * 1e-3), "unit": "pairs/s",
             "h2d_bytes_per_step": n * 2 * IN_W * IN_H * 4, "d2h_bytes_per_step": n * 2 * OUT_W * OUT_H * 4,
             "steps": steps, "wall_value": pairs / world / wall * world,
-            "note": "pinned host -> H2D -> EASU+RCAS -> D2H per eye via ovrfsr_apply_host, 2 streams"}
+            "note": "pinned host -> H2D -> EASU+RCAS -> D2H per eye via ovrfsr_apply_host; 2 contexts x 2 streams in flight"}
 
 
 if __name__ == "__main__":

@@ -50,7 +50,10 @@ typedef enum ovrfsr_format {
   OVRFSR_FORMAT_RGBA16F = 2, /* DXGI_FORMAT_R16G16B16A16_FLOAT */
   OVRFSR_FORMAT_RGBA32F = 3, /* DXGI_FORMAT_R32G32B32A32_FLOAT (input: PostProcessor.cpp:32-33; as an output it
                                 exposes the pre-quantisation result) */
-  OVRFSR_FORMAT_AUTO = -1    /* output only: DetermineOutputFormat(), :63-74 -> RGBA8 */
+  OVRFSR_FORMAT_RGB10A2 = 4, /* DXGI_FORMAT_R10G10B10A2_UNORM: one little-endian u32 per texel, R bits 0-9, G 10-19,
+                                B 20-29, A 30-31.  As an output it is only produced from an RGB10A2 source -- the case
+                                DetermineOutputFormat() exists for (:63-74) */
+  OVRFSR_FORMAT_AUTO = -1    /* output only: DetermineOutputFormat(), :63-74 -> RGB10A2 for an RGB10A2 source, else RGBA8 */
 } ovrfsr_format;
 
 /* arithmetic mode of the kernels */

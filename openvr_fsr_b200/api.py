@@ -147,14 +147,15 @@ class PostProcessor:
         if rc == L.PASSTHROUGH:
             return texture
         L.check(rc, "ovrfsr_apply", self._ctx)
+        self.last_output_format = out.format  # RGBA8, or RGB10A2 for a 10-bit source (bytes of the packed u32 texels)
         return _wrap_device(out, texture.device)
 
     def apply_host(self, eye: int, src_host, dst_host, bounds: TextureBounds | None = None, fmt: int | None = None,
-                   stream=None):
+                   stream=None, dst_fmt: int | None = None):
         """End-to-end entry: host (pinned) tensors in and out, copies included, asynchronous on `stream`."""
         bounds = bounds or TextureBounds()
         only_one_eye = int(abs(bounds.uMax - bounds.uMin) > 0.5)
-        s, d = image_of(src_host, fmt), image_of(dst_host)
+        s, d = image_of(src_host, fmt), image_of(dst_host, dst_fmt)
         L.check(L.lib().ovrfsr_apply_host(self._ctx, eye, C.byref(s), only_one_eye, C.byref(d), _stream_ptr(stream)),
                 "ovrfsr_apply_host", self._ctx)
 
@@ -194,30 +195,30 @@ def _wrap_device(img: L.Image, device):
 
 
 # ---- the individual dispatches (ApplyUpscaling / ApplySharpening) on tensors ---------------------------
-def _dispatch(fn, src, dst, consts, math_mode, stream, src_fmt=None):
-    s, d = image_of(src, src_fmt), image_of(dst)
+def _dispatch(fn, src, dst, consts, math_mode, stream, src_fmt=None, dst_fmt=None):
+    s, d = image_of(src, src_fmt), image_of(dst, dst_fmt)
     L.check(fn(C.byref(s), C.byref(d), consts, math_mode, _stream_ptr(stream)), fn.__name__)
     return dst
 
 
-def fsr_easu(src, dst, consts24, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+def fsr_easu(src, dst, consts24, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):
     c = (C.c_uint32 * 24)(*[int(x) for x in consts24])
-    return _dispatch(L.lib().ovrfsr_dispatch_fsr_easu, src, dst, c, math_mode, stream, src_fmt)
+    return _dispatch(L.lib().ovrfsr_dispatch_fsr_easu, src, dst, c, math_mode, stream, src_fmt, dst_fmt)
 
 
-def fsr_rcas(src, dst, consts12, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+def fsr_rcas(src, dst, consts12, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):
     c = (C.c_uint32 * 12)(*[int(x) for x in consts12])
-    return _dispatch(L.lib().ovrfsr_dispatch_fsr_rcas, src, dst, c, math_mode, stream, src_fmt)
+    return _dispatch(L.lib().ovrfsr_dispatch_fsr_rcas, src, dst, c, math_mode, stream, src_fmt, dst_fmt)
 
 
-def nis_scaler(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+def nis_scaler(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):
     buf = C.create_string_buffer(bytes(cfg256), 256)
-    return _dispatch(L.lib().ovrfsr_dispatch_nis_scaler, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt)
+    return _dispatch(L.lib().ovrfsr_dispatch_nis_scaler, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt, dst_fmt)
 
 
-def nis_sharpen(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None):
+def nis_sharpen(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):
     buf = C.create_string_buffer(bytes(cfg256), 256)
-    return _dispatch(L.lib().ovrfsr_dispatch_nis_sharpen, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt)
+    return _dispatch(L.lib().ovrfsr_dispatch_nis_sharpen, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt, dst_fmt)
 
 
 def make_upscale_constants(cfg: Config, eye, only_one_eye, in_w, in_h, out_w, out_h) -> np.ndarray:

@@ -23,7 +23,7 @@ namespace {
 constexpr int kQueryCount = 6; // QUERY_COUNT, PostProcessor.h:78
 
 inline uint32_t bytes_per_pixel(int fmt) { return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u); }
-inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGBA32F; }
+inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGB10A2; }
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 struct DeviceImage {
@@ -39,6 +39,43 @@ struct DeviceImage {
     img = ovrfsr_image{};
   }
 };
+
+// linear device scratch for the host entry: PCIe copies are issued as ONE contiguous cudaMemcpyAsync each way
+// (2-D pitched copies in opposite directions were measured not to overlap on B200: 795 pairs/s vs 1100) and a
+// small kernel moves rows between the tight host layout and the 256-byte-pitched device images.
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  bool ensure(size_t n) {
+    if (n <= bytes) return true;
+    release();
+    if (cudaMalloc(&ptr, n) != cudaSuccess) { ptr = nullptr; return false; }
+    bytes = n;
+    return true;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+  }
+};
+
+// rows of `rowWords` 32-bit words from pitch `spitch` to pitch `dpitch` (bytes, multiples of 4); HBM-bound, ~10 us/eye
+__global__ void __launch_bounds__(256) repitch_rows_kernel(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *__restrict__ src,
+                                                           size_t spitch, uint32_t rowWords, uint32_t rows) {
+  for (uint32_t y = blockIdx.y; y < rows; y += gridDim.y) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (size_t)y * spitch);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch);
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < rowWords; x += gridDim.x * blockDim.x) d[x] = s[x];
+  }
+}
+
+cudaError_t repitch_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t rowBytes, uint32_t rows, cudaStream_t s) {
+  const uint32_t rowWords = (uint32_t)(rowBytes / 4);
+  dim3 grid((rowWords + 1023) / 1024, rows < 4096 ? rows : 4096);
+  repitch_rows_kernel<<<grid, 256, 0, s>>>(static_cast<uint8_t *>(dst), dpitch, static_cast<const uint8_t *>(src), spitch, rowWords, rows);
+  count_launch();
+  return cudaGetLastError();
+}
 
 PassImage pass_image(const ovrfsr_image &im, int slice = 0) {
   PassImage p;
@@ -66,6 +103,7 @@ struct ovrfsr_ctx {
   // one set of intermediates/outputs PER EYE (the reference shares one; see ovrfsr.h)
   DeviceImage upscaled[2], sharpened[2];
   DeviceImage hostStage[2]; // device staging of host-submitted eyes (ovrfsr_apply_host)
+  DeviceBuffer hostLinearIn[2], hostLinearOut[2];
   const void *lastSubmittedTexture = nullptr;
   ovrfsr_image lastOutput{};
   int eyeCount = 0;
@@ -90,7 +128,7 @@ int fail(ovrfsr_ctx *ctx, int status, const char *what, cudaError_t e = cudaSucc
 }
 
 void release_resources(ovrfsr_ctx *c) {
-  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); }
+  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); c->hostLinearIn[e].release(); c->hostLinearOut[e].release(); }
   if (c->evCreated) {
     for (int i = 0; i < kQueryCount; ++i) { cudaEventDestroy(c->evStart[i]); cudaEventDestroy(c->evEnd[i]); c->evPending[i] = false; }
     c->evCreated = false;
@@ -115,10 +153,14 @@ int prepare_resources(ovrfsr_ctx *c, const ovrfsr_image *src) {
   c->inFormat = src->format;
   host::output_size(src->width, src->height, c->cfg.render_scale, &c->outputWidth, &c->outputHeight);
   if (c->outputWidth == 0 || c->outputHeight == 0) return fail(c, OVRFSR_ERR_INVALID, "output size is zero");
-  // DetermineOutputFormat (PostProcessor.cpp:63-74): RGBA8 unless the caller asks for the FP16 extension
-  c->outFormat = c->cfg.output_format == OVRFSR_FORMAT_AUTO ? OVRFSR_FORMAT_RGBA8 : c->cfg.output_format;
-  if (c->outFormat != OVRFSR_FORMAT_RGBA8 && c->outFormat != OVRFSR_FORMAT_RGBA16F && c->outFormat != OVRFSR_FORMAT_RGBA32F)
-    return fail(c, OVRFSR_ERR_UNSUPPORTED, "output format must be RGBA8, RGBA16F or RGBA32F");
+  // DetermineOutputFormat (PostProcessor.cpp:63-74): 10-bit sources keep a 10-bit target, everything else gets
+  // RGBA8, unless the caller asks for a float output (extension)
+  const bool tenBit = src->format == OVRFSR_FORMAT_RGB10A2;
+  c->outFormat = c->cfg.output_format == OVRFSR_FORMAT_AUTO ? (tenBit ? OVRFSR_FORMAT_RGB10A2 : OVRFSR_FORMAT_RGBA8) : c->cfg.output_format;
+  if (c->outFormat != OVRFSR_FORMAT_RGBA16F && c->outFormat != OVRFSR_FORMAT_RGBA32F &&
+      c->outFormat != (tenBit ? OVRFSR_FORMAT_RGB10A2 : OVRFSR_FORMAT_RGBA8))
+    return fail(c, OVRFSR_ERR_UNSUPPORTED, tenBit ? "output format for an RGB10A2 source must be RGB10A2, RGBA16F or RGBA32F"
+                                                  : "output format must be RGBA8, RGBA16F or RGBA32F");
   const bool one = c->textureContainsOnlyOneEye;
   const int neyes = one ? 2 : 1;
   for (int e = 0; e < neyes; ++e) {
@@ -339,16 +381,31 @@ int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, in
       return fail(ctx, OVRFSR_ERR_NOMEM, "allocating host staging image", cudaGetLastError());
   }
   const size_t rowBytes = (size_t)src_host->width * bytes_per_pixel(src_host->format);
-  cudaError_t e = cudaMemcpy2DAsync(st.img.data, st.img.pitch, src_host->data, src_host->pitch, rowBytes, src_host->height,
-                                    cudaMemcpyHostToDevice, s);
+  cudaError_t e;
+  if (src_host->pitch == rowBytes) { // tight host rows: one contiguous PCIe copy, re-pitched on the device
+    DeviceBuffer &lin = ctx->hostLinearIn[eye];
+    if (!lin.ensure(rowBytes * src_host->height)) return fail(ctx, OVRFSR_ERR_NOMEM, "allocating linear upload buffer", cudaGetLastError());
+    e = cudaMemcpyAsync(lin.ptr, src_host->data, rowBytes * src_host->height, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = repitch_rows(st.img.data, st.img.pitch, lin.ptr, rowBytes, rowBytes, src_host->height, s);
+  } else {
+    e = cudaMemcpy2DAsync(st.img.data, st.img.pitch, src_host->data, src_host->pitch, rowBytes, src_host->height,
+                          cudaMemcpyHostToDevice, s);
+  }
   if (e != cudaSuccess) return fail(ctx, OVRFSR_ERR_CUDA, "host->device copy", e);
   ovrfsr_image out{};
   rc = ovrfsr_apply(ctx, eye, &st.img, only_one_eye, &out, stream);
   if (rc != OVRFSR_OK) return rc;
   if (dst_host->width != out.width || dst_host->height != out.height || dst_host->format != out.format)
     return fail(ctx, OVRFSR_ERR_INVALID, "host destination does not match the output size/format");
-  e = cudaMemcpy2DAsync(dst_host->data, dst_host->pitch, out.data, out.pitch, (size_t)out.width * bytes_per_pixel(out.format),
-                        out.height, cudaMemcpyDeviceToHost, s);
+  const size_t outRowBytes = (size_t)out.width * bytes_per_pixel(out.format);
+  if (dst_host->pitch == outRowBytes && out.pitch != outRowBytes) {
+    DeviceBuffer &lin = ctx->hostLinearOut[eye];
+    if (!lin.ensure(outRowBytes * out.height)) return fail(ctx, OVRFSR_ERR_NOMEM, "allocating linear download buffer", cudaGetLastError());
+    e = repitch_rows(lin.ptr, outRowBytes, out.data, out.pitch, outRowBytes, out.height, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst_host->data, lin.ptr, outRowBytes * out.height, cudaMemcpyDeviceToHost, s);
+  } else {
+    e = cudaMemcpy2DAsync(dst_host->data, dst_host->pitch, out.data, out.pitch, outRowBytes, out.height, cudaMemcpyDeviceToHost, s);
+  }
   return e == cudaSuccess ? OVRFSR_OK : fail(ctx, OVRFSR_ERR_CUDA, "device->host copy", e);
 }
 
@@ -357,7 +414,10 @@ static int check_pair(const ovrfsr_image *src, const ovrfsr_image *dst) {
   int rc = validate_image(src);
   if (rc != OVRFSR_OK) return rc;
   if ((rc = validate_image(dst)) != OVRFSR_OK) return rc;
-  if (dst->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED; /* outputs are RGBA8 (reference) or float */
+  if (dst->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED; /* outputs are RGBA8 / RGB10A2 (reference) or float */
+  if ((dst->format == OVRFSR_FORMAT_RGB10A2) != (src->format == OVRFSR_FORMAT_RGB10A2) && dst->format != OVRFSR_FORMAT_RGBA16F &&
+      dst->format != OVRFSR_FORMAT_RGBA32F)
+    return OVRFSR_ERR_UNSUPPORTED; /* UNORM targets follow DetermineOutputFormat: 10-bit in <-> 10-bit out */
   return OVRFSR_OK;
 }
 

@@ -85,6 +85,26 @@ __device__ __forceinline__ float unorm8(float v) {
   return __fmaf_rn(e, r, q);
 }
 
+// UNORM10 / UNORM2 decode of DXGI_FORMAT_R10G10B10A2_UNORM: the same residual-corrected multiply, exact (= v/1023, v/3
+// correctly rounded) for all 1024 / 4 codes (tests/test_host_logic.py).
+__device__ __forceinline__ float unorm10(uint32_t v) {
+  const float r = 1.0f / 1023.0f, f = (float)v;
+  const float q = __fmul_rn(f, r);
+  return __fmaf_rn(__fmaf_rn(-1023.0f, q, f), r, q);
+}
+__device__ __forceinline__ float unorm2(uint32_t v) {
+  const float r = 1.0f / 3.0f, f = (float)v;
+  const float q = __fmul_rn(f, r);
+  return __fmaf_rn(__fmaf_rn(-3.0f, q, f), r, q);
+}
+__device__ __forceinline__ float4 decode_rgb10a2(uint32_t p) {
+  return make_float4(unorm10(p & 1023u), unorm10((p >> 10) & 1023u), unorm10((p >> 20) & 1023u), unorm2(p >> 30));
+}
+// formats stored as one 32-bit word per texel (the TMA tile loaders handle exactly these)
+__host__ __device__ constexpr bool packed32(int fmt) {
+  return fmt == OVRFSR_FORMAT_RGBA8 || fmt == OVRFSR_FORMAT_BGRA8 || fmt == OVRFSR_FORMAT_RGB10A2;
+}
+
 // Fast-math decode of byte K: PRMT builds the float 2^23+v, one FFMA computes (2^23+v)*r - 2^23*r = fl(v*r) with a
 // single rounding (2^23*r is exact).  Differs from the correctly rounded v/255 by at most 1 ulp (126 of 256 codes);
 // strict math always uses unorm8().
@@ -108,6 +128,8 @@ __device__ __forceinline__ float4 fetch_texel(const uint8_t *__restrict__ row, i
     const __half2 lo = *reinterpret_cast<const __half2 *>(&p.x), hi = *reinterpret_cast<const __half2 *>(&p.y);
     const float2 a = __half22float2(lo), b = __half22float2(hi);
     return make_float4(a.x, a.y, b.x, b.y);
+  } else if constexpr (FMT == OVRFSR_FORMAT_RGB10A2) {
+    return decode_rgb10a2(__ldg(reinterpret_cast<const uint32_t *>(row) + x));
   } else {
     const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(row) + x);
     const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p));
@@ -125,6 +147,15 @@ __device__ __forceinline__ uint32_t to_unorm8(float v) {
   else t = __fmaf_rn(s, 255.0f, 0.5f);
   return (uint32_t)t; // F2I.TRUNC; t is in [0.5, 255.5]
 }
+// FLOAT -> UNORM with MAXV = 2^n - 1 (1023, 3): (uint)(saturate(v)*MAXV + 0.5)
+template <int MAXV>
+__device__ __forceinline__ uint32_t to_unorm(float v) {
+  float s = __saturatef(v);
+  float t;
+  if constexpr (kStrict) t = __fadd_rn(__fmul_rn(s, (float)MAXV), 0.5f);
+  else t = __fmaf_rn(s, (float)MAXV, 0.5f);
+  return (uint32_t)t;
+}
 
 template <int FMT>
 __device__ __forceinline__ void store_texel(uint8_t *__restrict__ row, int x, float r, float g, float b, float a) {
@@ -136,6 +167,8 @@ __device__ __forceinline__ void store_texel(uint8_t *__restrict__ row, int x, fl
     p.x = *reinterpret_cast<const uint32_t *>(&lo);
     p.y = *reinterpret_cast<const uint32_t *>(&hi);
     reinterpret_cast<uint2 *>(row)[x] = p;
+  } else if constexpr (FMT == OVRFSR_FORMAT_RGB10A2) {
+    reinterpret_cast<uint32_t *>(row)[x] = to_unorm<1023>(r) | (to_unorm<1023>(g) << 10) | (to_unorm<1023>(b) << 20) | (to_unorm<3>(a) << 30);
   } else {
     const uint32_t p = to_unorm8(r) | (to_unorm8(g) << 8) | (to_unorm8(b) << 16) | (to_unorm8(a) << 24);
     reinterpret_cast<uint32_t *>(row)[x] = p;
@@ -150,6 +183,8 @@ __device__ __forceinline__ uint32_t pack_rgba8_opaque(float r, float g, float b)
 template <int FMT>
 __device__ __forceinline__ void store_opaque(uint8_t *__restrict__ row, int x, float r, float g, float b) {
   if constexpr (FMT == OVRFSR_FORMAT_RGBA8) reinterpret_cast<uint32_t *>(row)[x] = pack_rgba8_opaque(r, g, b);
+  else if constexpr (FMT == OVRFSR_FORMAT_RGB10A2)
+    reinterpret_cast<uint32_t *>(row)[x] = to_unorm<1023>(r) | (to_unorm<1023>(g) << 10) | (to_unorm<1023>(b) << 20) | 0xC0000000u;
   else store_texel<FMT>(row, x, r, g, b, 1.0f);
 }
 

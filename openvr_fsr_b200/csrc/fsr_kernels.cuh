@@ -301,12 +301,14 @@ __device__ __forceinline__ float3 easu_bilinear(const float4 *__restrict__ sC, i
 // result by several LSB at such pixels.
 template <int FMT>
 __device__ __forceinline__ float4 decode_rgb1(uint32_t p) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGB10A2) return make_float4(unorm10(p & 1023u), unorm10((p >> 10) & 1023u), unorm10((p >> 20) & 1023u), 1.0f);
   const float c0 = unorm8(byte_to_float<0>(p)), c1 = unorm8(byte_to_float<1>(p)), c2 = unorm8(byte_to_float<2>(p));
   if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, 1.0f);
   return make_float4(c0, c1, c2, 1.0f);
 }
 template <int FMT>
 __device__ __forceinline__ float4 decode_rgba(uint32_t p) {
+  if constexpr (FMT == OVRFSR_FORMAT_RGB10A2) return decode_rgb10a2(p);
   const float c0 = byte_to_unorm_mode<0>(p), c1 = byte_to_unorm_mode<1>(p);
   const float c2 = byte_to_unorm_mode<2>(p), c3 = byte_to_unorm_mode<3>(p);
   if constexpr (FMT == OVRFSR_FORMAT_BGRA8) return make_float4(c2, c1, c0, c3);
@@ -561,6 +563,8 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH;
   const int sx0 = ox0 - 1, sy0 = oy0 - 1;
+  // same UNORM layout in and out: outside-radius texels pass through bit for bit
+  constexpr bool kRawCopy = FIN == FOUT && (FIN == OVRFSR_FORMAT_RGBA8 || FIN == OVRFSR_FORMAT_RGB10A2);
 
   if constexpr (TMA) {
     if (tid == 0) {
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
 
   if constexpr (TMA) {
     // a CTA whose 8 groups are all outside the radius and copy raw bytes needs no decoded tile at all
-    const bool rawCopy = FIN == OVRFSR_FORMAT_RGBA8 && FOUT == OVRFSR_FORMAT_RGBA8 && a.tintGB == 1.0f;
+    const bool rawCopy = kRawCopy && a.tintGB == 1.0f;
     const int needTile = __syncthreads_or(inside || !rawCopy); // also orders the barrier init before the polls
     mbar_wait(&tileBar, 0);
     if (needTile)
@@ -614,10 +618,10 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
     }
   } else {
     // OutputTexture[p] = mul * InputTexture[p], alpha included (fsr_rcas.hlsl:45-53)
-    if constexpr (TMA && FIN == OVRFSR_FORMAT_RGBA8 && FOUT == OVRFSR_FORMAT_RGBA8) {
+    if constexpr (TMA && kRawCopy) {
       if (a.tintGB == 1.0f) {
-        // debug tint off: mul == 1 and decode -> x1 -> encode is the identity on all 256 codes (exhaustive check in
-        // tests/test_host_logic.py), so the texel bytes are copied straight from the TMA landing zone
+        // debug tint off: mul == 1 and decode -> x1 -> encode is the identity on all 256 (1024, 4) codes (exhaustive
+        // check in tests/test_host_logic.py), so the texel bits are copied straight from the TMA landing zone
         const uint32_t *q = sRaw + (y0 - sy0) * kRcasRawW + (x - sx0) + 3;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {

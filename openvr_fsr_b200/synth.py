@@ -58,3 +58,30 @@ def stereo_pair(kind: str, w: int, h: int, seed: int = 0):
     gen = {"uniform": uniform_rgba8, "natural": natural_rgba8, "natural16f": natural_rgba16f}[kind]
     left = gen(w, h, seed)
     return left, np.ascontiguousarray(np.roll(left, 16, axis=1))
+
+
+def pack_rgb10a2(rgb10: np.ndarray, a2: np.ndarray) -> np.ndarray:
+    """(H, W, 3) values 0..1023 and (H, W) values 0..3 -> (H, W, 4) uint8 = the bytes of the little-endian
+    R10G10B10A2 word per texel (R bits 0-9, G 10-19, B 20-29, A 30-31)."""
+    w = (rgb10[..., 0].astype(np.uint32) | (rgb10[..., 1].astype(np.uint32) << 10) |
+         (rgb10[..., 2].astype(np.uint32) << 20) | (a2.astype(np.uint32) << 30))
+    return np.ascontiguousarray(w.astype("<u4")).view(np.uint8).reshape(w.shape[0], w.shape[1], 4)
+
+
+def unpack_rgb10a2(img: np.ndarray) -> np.ndarray:
+    """(H, W, 4) uint8 bytes of R10G10B10A2 words -> (H, W, 4) int32 channel codes (r, g, b, a)."""
+    w = np.ascontiguousarray(img).view("<u4").reshape(img.shape[0], img.shape[1]).astype(np.uint32)
+    return np.stack([w & 1023, (w >> 10) & 1023, (w >> 20) & 1023, w >> 30], axis=-1).astype(np.int32)
+
+
+def natural_rgb10a2(width: int, height: int, seed: int) -> np.ndarray:
+    """The natural_rgba16f scene quantised to R10G10B10A2_UNORM (as bytes, see pack_rgb10a2)."""
+    f = np.clip(natural_rgba16f(width, height, seed).astype(np.float32), 0.0, 1.0)
+    rng = np.random.default_rng(seed + 77)
+    rgb = np.floor(f[..., :3] * 1023.0 + 0.5).astype(np.uint32)
+    return pack_rgb10a2(rgb, rng.integers(0, 4, size=(height, width)))
+
+
+def uniform_rgb10a2(width: int, height: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return pack_rgb10a2(rng.integers(0, 1024, size=(height, width, 3)), rng.integers(0, 4, size=(height, width)))

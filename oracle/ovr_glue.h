@@ -72,6 +72,11 @@ static inline void ovo_texel(const ovo_image *im, int x, int y, float o[4]) {
     const uint16_t *p = (const uint16_t *)(row + (size_t)x * 8);
     o[0] = ovo_half_to_float(p[0]); o[1] = ovo_half_to_float(p[1]);
     o[2] = ovo_half_to_float(p[2]); o[3] = ovo_half_to_float(p[3]);
+  } else if (im->format == OVO_FMT_RGB10A2) {
+    uint32_t p;
+    memcpy(&p, row + (size_t)x * 4, 4);
+    o[0] = (float)(p & 1023u) / 1023.0f; o[1] = (float)((p >> 10) & 1023u) / 1023.0f;
+    o[2] = (float)((p >> 20) & 1023u) / 1023.0f; o[3] = (float)(p >> 30) / 3.0f;
   } else {
     const uint8_t *p = row + (size_t)x * 4;
     float a = (float)p[0] / 255.0f, b = (float)p[1] / 255.0f, c = (float)p[2] / 255.0f;
@@ -127,6 +132,10 @@ static inline void ovo_store(const ovo_image *im, int x, int y, const float c[4]
   } else if (im->format == OVO_FMT_RGBA16F) {
     uint16_t *p = (uint16_t *)(row + (size_t)x * 8);
     for (int i = 0; i < 4; ++i) p[i] = ovo_float_to_half(c[i]);
+  } else if (im->format == OVO_FMT_RGB10A2) {
+    uint32_t p = (uint32_t)(ovo_sat(c[0]) * 1023.0f + 0.5f) | ((uint32_t)(ovo_sat(c[1]) * 1023.0f + 0.5f) << 10) |
+                 ((uint32_t)(ovo_sat(c[2]) * 1023.0f + 0.5f) << 20) | ((uint32_t)(ovo_sat(c[3]) * 3.0f + 0.5f) << 30);
+    memcpy(row + (size_t)x * 4, &p, 4);
   } else {
     uint8_t *p = row + (size_t)x * 4;
     uint8_t q[4];

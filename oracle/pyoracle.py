@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-FMT_RGBA8, FMT_BGRA8, FMT_RGBA16F, FMT_RGBA32F = 0, 1, 2, 3
+FMT_RGBA8, FMT_BGRA8, FMT_RGBA16F, FMT_RGBA32F, FMT_RGB10A2 = 0, 1, 2, 3, 4
 
 
 class Image(C.Structure):

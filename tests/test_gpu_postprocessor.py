@@ -113,3 +113,25 @@ def test_apply_host_roundtrip(cuda):
     torch.cuda.synchronize()
     assert np.array_equal(dst.numpy(), _oracle_fsr(img, 0, True, 0.75, 0.5, 0.9))
     pp.close()
+
+
+def test_apply_host_pitched_host_rows(cuda):
+    """Host images whose rows are padded take the 2-D copy path; the padding bytes must stay untouched."""
+    import torch
+    import openvr_fsr_b200 as ovr
+    from openvr_fsr_b200 import synth
+    from oracle import pyoracle as po
+    img = synth.natural_rgba8(301, 211, 9)
+    ow, oh = po.output_size(301, 211, 0.75)
+    sbuf = torch.zeros((211, 301 * 4 + 60), dtype=torch.uint8).pin_memory()
+    dbuf = torch.full((oh, ow * 4 + 100), 0xAB, dtype=torch.uint8).pin_memory()
+    src = torch.as_strided(sbuf, (211, 301, 4), (sbuf.stride(0), 4, 1))
+    dst = torch.as_strided(dbuf, (oh, ow, 4), (dbuf.stride(0), 4, 1))
+    src.copy_(torch.from_numpy(img))
+    pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=0.75, sharpness=0.9, radius=0.5))
+    for eye in (0, 1, 0):  # also re-use of the staging buffers
+        pp.apply_host(eye, src, dst)
+        torch.cuda.synchronize()
+        assert np.array_equal(dst.numpy(), _oracle_fsr(img, eye, True, 0.75, 0.5, 0.9))
+        assert bool((dbuf[:, ow * 4:] == 0xAB).all())
+    pp.close()

@@ -120,6 +120,37 @@ def test_unorm8_decode_recipe_is_exact():
     assert np.array_equal((np.clip(q2, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8), np.arange(256))
 
 
+def test_unorm10_decode_recipe_is_exact():
+    """device_common.cuh unorm10()/unorm2(): the same residual-corrected multiply must give the correctly rounded
+    v/1023 (v/3) for all 1024 (4) codes, and encode(decode(v)) == v (RCAS's raw pass-through on RGB10A2)."""
+    for maxv in (1023, 3):
+        v = np.arange(maxv + 1, dtype=np.float64)
+        r = np.float64(np.float32(1.0) / np.float32(maxv))
+        q = (v * r).astype(np.float32).astype(np.float64)
+        e = (v - maxv * q).astype(np.float32).astype(np.float64)
+        q2 = (e * r + q).astype(np.float32)
+        assert np.array_equal(q2, np.arange(maxv + 1, dtype=np.float32) / np.float32(maxv))
+        assert np.array_equal((np.clip(q2, 0, 1) * np.float32(maxv) + np.float32(0.5)).astype(np.uint32), np.arange(maxv + 1))
+
+
+def test_rgb10a2_pack_roundtrip_and_oracle_decode():
+    """synth's R10G10B10A2 packing is the layout the oracle decodes: an RCAS whose radius mask excludes every group
+    is the identity on 10-bit texels (decode -> x1 -> encode), alpha included."""
+    from openvr_fsr_b200 import synth
+    from oracle import pyoracle as po
+    img = synth.uniform_rgb10a2(40, 24, 3)
+    codes = synth.unpack_rgb10a2(img)
+    assert codes[..., :3].max() <= 1023 and codes[..., 3].max() <= 3
+    assert np.array_equal(synth.pack_rgb10a2(codes[..., :3], codes[..., 3]), img)
+    sc = po.sharpen_constants(0, True, 40, 24, radius=0.0, sharpness=0.9, proj=(5.0, 5.0, 5.0, 5.0))
+    out = po.rcas(img, sc, src_fmt=po.FMT_RGB10A2, dst_fmt=po.FMT_RGB10A2)
+    assert np.array_equal(out, img)
+    # and a float view of the same texels: code / 1023, alpha / 3
+    f = po.rcas(img, sc, out_dtype=np.float32, src_fmt=po.FMT_RGB10A2)
+    assert np.array_equal(f[..., :3], codes[..., :3].astype(np.float32) / np.float32(1023.0))
+    assert np.array_equal(f[..., 3], codes[..., 3].astype(np.float32) / np.float32(3.0))
+
+
 def test_passthrough_and_loud_failure_without_gpu():
     import torch
     tex = torch.zeros((8, 8, 4), dtype=torch.uint8)

@@ -47,6 +47,22 @@ def test_fsr_formats_bit_identical():
             assert np.array_equal(c.view(np.uint8), d.view(np.uint8))
 
 
+def test_fsr_rgb10a2_bit_identical():
+    """10-bit sources keep a 10-bit target (DetermineOutputFormat, PostProcessor.cpp:63-74)."""
+    iw, ih, scale = 41, 33, 0.75
+    ow, oh = po.output_size(iw, ih, scale)
+    uc = po.upscale_constants(0, True, iw, ih, ow, oh, radius=0.45)
+    sc = po.sharpen_constants(0, True, ow, oh, radius=0.45, sharpness=0.8)
+    from openvr_fsr_b200 import synth
+    src = synth.natural_rgb10a2(iw, ih, 6)
+    kw = dict(src_fmt=po.FMT_RGB10A2, dst_fmt=po.FMT_RGB10A2)
+    a, b = po.easu(src, ow, oh, uc, **kw), po.easu(src, ow, oh, uc, which="ref", **kw)
+    assert np.array_equal(a, b)
+    assert (synth.unpack_rgb10a2(a)[..., 3] == 3).all()  # EASU writes alpha 1
+    assert ((synth.unpack_rgb10a2(a)[..., 0] * 255) % 1023 != 0).any()  # codes that no 8-bit value maps to
+    assert np.array_equal(po.rcas(a, sc, **kw), po.rcas(a, sc, which="ref", **kw))
+
+
 def test_threads_do_not_change_results():
     iw, ih = 65, 43
     ow, oh = po.output_size(iw, ih, 0.75)

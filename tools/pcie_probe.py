@@ -20,3 +20,30 @@ def both():
     with torch.cuda.stream(s1): dc.copy_(hp, non_blocking=True)
     with torch.cuda.stream(s2): hp2.copy_(dc2, non_blocking=True)
 print("bidirectional contiguous GB/s (sum)", bw(both, 2 * H * W))
+
+# pipeline shaped like ovrfsr_apply_host: per stream H2D(in eye) -> [kernel] -> D2H(out eye), round-robin over S streams
+IH, IW, OH, OW = 1869, 1683 * 4, 2492, 2244 * 4
+def pipeline(S, pitched, nframes=16, busy=False):
+    ss = [torch.cuda.Stream() for _ in range(S)]
+    hin = [torch.empty((IH, IW), dtype=torch.uint8).pin_memory() for _ in range(S)]
+    hout = [torch.empty((OH, OW), dtype=torch.uint8).pin_memory() for _ in range(S)]
+    if pitched:
+        din = [torch.empty((IH, 6912), dtype=torch.uint8, device=dev)[:, :IW] for _ in range(S)]
+        dout = [torch.empty((OH, 9216), dtype=torch.uint8, device=dev)[:, :OW] for _ in range(S)]
+    else:
+        din = [torch.empty((IH, IW), dtype=torch.uint8, device=dev) for _ in range(S)]
+        dout = [torch.empty((OH, OW), dtype=torch.uint8, device=dev) for _ in range(S)]
+    def run():
+        for f in range(nframes * 2):
+            k = f % S
+            with torch.cuda.stream(ss[k]):
+                din[k].copy_(hin[k], non_blocking=True)
+                if busy: torch.cuda._sleep(250000)   # ~0.13 ms of "kernel"
+                hout[k].copy_(dout[k], non_blocking=True)
+    run(); torch.cuda.synchronize(); t = time.perf_counter()
+    run(); torch.cuda.synchronize(); dt = time.perf_counter() - t
+    return nframes / dt
+for S in (1, 2, 4, 8):
+    for pitched in (False, True):
+        for busy in (False, True):
+            print(f"pipeline streams={S} pitched={pitched} kernel={busy}: {pipeline(S, pitched, busy=busy):.0f} pairs/s")
