@@ -76,6 +76,9 @@ typedef struct ovrfsr_image {
   int32_t format;       /* ovrfsr_format */
   uint32_t array_slices;/* >1: right eye lives in slice 1 (PostProcessor.cpp:254-268); 0 is treated as 1 */
   uint32_t slice_pitch; /* bytes between slices when array_slices > 1 */
+  uint32_t sample_count;/* >1: multisampled source (D3D11_TEXTURE2D_DESC::SampleDesc.Count): the samples of one texel
+                           are consecutive, row = width*sample_count texel-sized entries; ovrfsr_apply resolves it
+                           first like GetInputView's ResolveSubresource (PostProcessor.cpp:219-226).  0 = 1. */
 } ovrfsr_image;
 
 /* The Config fields that steer the path (src/postprocess/Config.h:11-17) plus what the
@@ -188,6 +191,37 @@ OVRFSR_API uint32_t ovrfsr_version(void);
 /* device image helpers (cudaMalloc with a 256-byte-aligned pitch, cudaFree) */
 OVRFSR_API int ovrfsr_image_alloc(ovrfsr_image *img, uint32_t width, uint32_t height, int32_t format);
 OVRFSR_API void ovrfsr_image_free(ovrfsr_image *img);
+
+
+/* ---- the callers either side of the path -------------------------- */
+/* GetInputView's MSAA branch (PostProcessor.cpp:219-226, ResolveSubresource): dst[x,y] = mean of the
+ * sample_count samples of texel (x,y), same format in and out; src_samples laid out as ovrfsr_image::sample_count
+ * describes (its width is the texel width).  Asynchronous on `stream`. */
+OVRFSR_API int ovrfsr_resolve_msaa(const ovrfsr_image *src_samples, const ovrfsr_image *dst, void *stream);
+/* IVRSystem_GetRecommendedRenderTargetSize detour (VrHooks.cpp:37-48): in/out the runtime's recommendation; scaled
+ * by renderScale when fsr_enabled and renderScale < 1 (u32 *= float, truncating). */
+OVRFSR_API void ovrfsr_recommended_render_size(const ovrfsr_config *cfg, uint32_t *width, uint32_t *height);
+/* the MIP LOD bias handed to the sampler hook: -log2(outputWidth / (float)inputWidth), PostProcessor.cpp:537-538 */
+OVRFSR_API float ovrfsr_mip_lod_bias(uint32_t input_width, uint32_t output_width);
+/* D3D11Context_PSSetSamplers' rule (VrHooks.cpp:123-128): the bias a replacement sampler gets -- added only to
+ * samplers without a bias of their own that filter anisotropically. */
+OVRFSR_API float ovrfsr_sampler_lod_bias(float sampler_mip_lod_bias, uint32_t sampler_max_anisotropy, float mip_lod_bias);
+
+/* F7 capture (PostProcessor.cpp:630-657): the next apply for the LEFT eye writes its output image to
+ * <directory>/capture_<YYYYmmdd_HHMMSS>_<fsr|nis>_s<sharpness*100>_r<radius*100>.dds and clears the request.
+ * That apply synchronises the stream (the reference's SaveDDSTextureToFile maps a staging copy). */
+OVRFSR_API int ovrfsr_request_capture(ovrfsr_ctx *ctx, const char *directory);
+OVRFSR_API const char *ovrfsr_last_capture_path(const ovrfsr_ctx *ctx);
+/* file name part of SaveTextureToFile (:641-652) for a given local time (seconds since the epoch) */
+OVRFSR_API int ovrfsr_capture_filename(const ovrfsr_config *cfg, int64_t unix_time, char *buf, uint32_t buf_size);
+/* DDS container exactly as ScreenGrab11's SaveDDSTextureToFile lays it out (ScreenGrab11.cpp:815-935): RGBA8 with
+ * the legacy A8B8G8R8 masks, BGRA8 with A8R8G8B8, RGBA16F / RGBA32F as D3DFMT FourCC 113 / 116, RGB10A2 through the
+ * 'DX10' extension header (dxgiFormat 24); one mip, tight rows.
+ * host_image->data is HOST memory.  ovrfsr_dds_read allocates host_image->data (release with ovrfsr_host_free), so
+ * a capture taken on a real D3D11 box can be diffed against this library's output. */
+OVRFSR_API int ovrfsr_dds_write(const char *path, const ovrfsr_image *host_image);
+OVRFSR_API int ovrfsr_dds_read(const char *path, ovrfsr_image *host_image);
+OVRFSR_API void ovrfsr_host_free(void *p);
 
 #ifdef __cplusplus
 }

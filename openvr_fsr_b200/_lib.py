@@ -15,7 +15,8 @@ MATH_FAST, MATH_STRICT = 0, 1
 
 class Image(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32),
-                ("format", C.c_int32), ("array_slices", C.c_uint32), ("slice_pitch", C.c_uint32)]
+                ("format", C.c_int32), ("array_slices", C.c_uint32), ("slice_pitch", C.c_uint32),
+                ("sample_count", C.c_uint32)]
 
 
 class Config(C.Structure):
@@ -58,6 +59,16 @@ SYMBOLS = {
     "ovrfsr_version": (C.c_uint32, []),
     "ovrfsr_image_alloc": (C.c_int, [_imgp, C.c_uint32, C.c_uint32, C.c_int32]),
     "ovrfsr_image_free": (None, [_imgp]),
+    "ovrfsr_resolve_msaa": (C.c_int, [_imgp, _imgp, _vp]),
+    "ovrfsr_recommended_render_size": (None, [_cfgp, _u32p, _u32p]),
+    "ovrfsr_mip_lod_bias": (C.c_float, [C.c_uint32, C.c_uint32]),
+    "ovrfsr_sampler_lod_bias": (C.c_float, [C.c_float, C.c_uint32, C.c_float]),
+    "ovrfsr_request_capture": (C.c_int, [_vp, C.c_char_p]),
+    "ovrfsr_last_capture_path": (C.c_char_p, [_vp]),
+    "ovrfsr_capture_filename": (C.c_int, [_cfgp, C.c_int64, C.c_char_p, C.c_uint32]),
+    "ovrfsr_dds_write": (C.c_int, [C.c_char_p, _imgp]),
+    "ovrfsr_dds_read": (C.c_int, [C.c_char_p, _imgp]),
+    "ovrfsr_host_free": (None, [_vp]),
 }
 
 _lib = None

@@ -63,12 +63,15 @@ def _format_of(t) -> int:
     raise TypeError("eye textures are uint8 (RGBA8/BGRA8), float16 (RGBA16F) or float32 (RGBA32F) tensors (H, W, 4)")
 
 
-def image_of(t, fmt: int | None = None) -> L.Image:
-    """Describe a (H, W, 4) tensor (CUDA or pinned host) as an ovrfsr_image; rows may be strided."""
+def image_of(t, fmt: int | None = None, samples: int = 1) -> L.Image:
+    """Describe a (H, W, 4) tensor (CUDA or pinned host) as an ovrfsr_image; rows may be strided.  With
+    samples > 1 the tensor is (H, W * samples, 4): the samples of one texel are consecutive (multisampled source)."""
     if t.dim() != 3 or t.shape[2] != 4 or t.stride(2) != 1 or t.stride(1) != 4:
         raise ValueError("expected a (H, W, 4) tensor with packed pixels")
-    return L.Image(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0) * t.element_size(),
-                   _format_of(t) if fmt is None else fmt, 1, 0)
+    if samples > 1 and t.shape[1] % samples:
+        raise ValueError("row length is not a multiple of the sample count")
+    return L.Image(t.data_ptr(), t.shape[1] // max(samples, 1), t.shape[0], t.stride(0) * t.element_size(),
+                   _format_of(t) if fmt is None else fmt, 1, 0, samples if samples > 1 else 0)
 
 
 def alloc_image(width: int, height: int, dtype=None, device="cuda", align: int = 256):
@@ -136,13 +139,15 @@ class PostProcessor:
         self.config = config
         L.check(L.lib().ovrfsr_set_config(self._ctx, C.byref(config.to_c())), "ovrfsr_set_config", self._ctx)
 
-    def apply(self, eye: int, texture, bounds: TextureBounds | None = None, fmt: int | None = None, stream=None):
+    def apply(self, eye: int, texture, bounds: TextureBounds | None = None, fmt: int | None = None, stream=None,
+              samples: int = 1):
         """vr::PostProcessor::Apply.  Returns a torch tensor VIEW of the ctx-owned output (valid until the next
-        apply for this eye / reset), or `texture` itself on pass-through."""
+        apply for this eye / reset), or `texture` itself on pass-through.  samples > 1: `texture` is a multisampled
+        source (see image_of) and is resolved first, as GetInputView does."""
         import torch
         bounds = bounds or TextureBounds()
         only_one_eye = int(abs(bounds.uMax - bounds.uMin) > 0.5)  # PostProcessor.cpp:146
-        src, out = image_of(texture, fmt), L.Image()
+        src, out = image_of(texture, fmt, samples), L.Image()
         rc = L.lib().ovrfsr_apply(self._ctx, eye, C.byref(src), only_one_eye, C.byref(out), _stream_ptr(stream))
         if rc == L.PASSTHROUGH:
             return texture
@@ -158,6 +163,13 @@ class PostProcessor:
         s, d = image_of(src_host, fmt), image_of(dst_host, dst_fmt)
         L.check(L.lib().ovrfsr_apply_host(self._ctx, eye, C.byref(s), only_one_eye, C.byref(d), _stream_ptr(stream)),
                 "ovrfsr_apply_host", self._ctx)
+
+    def request_capture(self, directory: str = ""):
+        """The F7 hotkey (PostProcessor.cpp:699-702): the next left-eye apply writes its output as a DDS file."""
+        L.check(L.lib().ovrfsr_request_capture(self._ctx, directory.encode()), "ovrfsr_request_capture", self._ctx)
+
+    def last_capture_path(self) -> str:
+        return L.lib().ovrfsr_last_capture_path(self._ctx).decode()
 
     def upscale_constants(self, eye: int) -> np.ndarray:
         w = (C.c_uint32 * 24)()
@@ -219,6 +231,58 @@ def nis_scaler(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_
 def nis_sharpen(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):
     buf = C.create_string_buffer(bytes(cfg256), 256)
     return _dispatch(L.lib().ovrfsr_dispatch_nis_sharpen, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt, dst_fmt)
+
+
+def resolve_msaa(src_samples, dst, samples: int, stream=None, fmt=None):
+    """GetInputView's ResolveSubresource (PostProcessor.cpp:219-226): (H, W*samples, 4) -> (H, W, 4) mean."""
+    s, d = image_of(src_samples, fmt, samples), image_of(dst, fmt)
+    L.check(L.lib().ovrfsr_resolve_msaa(C.byref(s), C.byref(d), _stream_ptr(stream)), "ovrfsr_resolve_msaa")
+    return dst
+
+
+def recommended_render_size(cfg: Config, width: int, height: int) -> tuple[int, int]:
+    """IVRSystem_GetRecommendedRenderTargetSize detour, VrHooks.cpp:37-48"""
+    w, h = C.c_uint32(width), C.c_uint32(height)
+    L.lib().ovrfsr_recommended_render_size(C.byref(cfg.to_c()), C.byref(w), C.byref(h))
+    return w.value, h.value
+
+
+def mip_lod_bias(input_width: int, output_width: int) -> float:
+    """PostProcessor.cpp:537-538"""
+    return L.lib().ovrfsr_mip_lod_bias(input_width, output_width)
+
+
+def sampler_lod_bias(sampler_bias: float, max_anisotropy: int, bias: float) -> float:
+    """VrHooks.cpp:123-128"""
+    return L.lib().ovrfsr_sampler_lod_bias(sampler_bias, max_anisotropy, bias)
+
+
+def capture_filename(cfg: Config, unix_time: int) -> str:
+    """PostProcessor.cpp:641-652"""
+    buf = C.create_string_buffer(96)
+    L.check(L.lib().ovrfsr_capture_filename(C.byref(cfg.to_c()), int(unix_time), buf, 96), "ovrfsr_capture_filename")
+    return buf.value.decode()
+
+
+def save_dds(path: str, array: np.ndarray, fmt: int | None = None):
+    """Write a HOST (H, W, 4) array as the DDS file the F7 capture produces (ScreenGrab11.cpp:815-935)."""
+    a = np.ascontiguousarray(array)
+    f = fmt if fmt is not None else {np.dtype(np.float16): L.FORMAT_RGBA16F, np.dtype(np.float32): L.FORMAT_RGBA32F}.get(a.dtype, L.FORMAT_RGBA8)
+    img = L.Image(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], f, 1, 0, 0)
+    L.check(L.lib().ovrfsr_dds_write(str(path).encode(), C.byref(img)), "ovrfsr_dds_write")
+
+
+def load_dds(path: str) -> tuple[np.ndarray, int]:
+    """Read such a file back: ((H, W, 4) array, ovrfsr_format)."""
+    img = L.Image()
+    L.check(L.lib().ovrfsr_dds_read(str(path).encode(), C.byref(img)), "ovrfsr_dds_read")
+    try:
+        dt = {L.FORMAT_RGBA16F: np.float16, L.FORMAT_RGBA32F: np.float32}.get(img.format, np.uint8)
+        n = img.pitch * img.height
+        raw = np.frombuffer(C.string_at(img.data, n), dtype=np.uint8).copy()
+        return raw.view(dt).reshape(img.height, img.width, 4), img.format
+    finally:
+        L.lib().ovrfsr_host_free(img.data)
 
 
 def make_upscale_constants(cfg: Config, eye, only_one_eye, in_w, in_h, out_w, out_h) -> np.ndarray:

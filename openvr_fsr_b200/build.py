@@ -23,6 +23,7 @@ UNITS = {
     "capi.cu": [],
     "nis_capi.cu": [],
     "postprocessor.cpp": [],
+    "capture.cpp": [],
 }
 
 

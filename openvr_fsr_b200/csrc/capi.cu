@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <ctime>
 #include <string>
+#include <vector>
 
 #include "host_constants.h"
 #include "kernels.h"
@@ -104,6 +106,10 @@ struct ovrfsr_ctx {
   DeviceImage upscaled[2], sharpened[2];
   DeviceImage hostStage[2]; // device staging of host-submitted eyes (ovrfsr_apply_host)
   DeviceBuffer hostLinearIn[2], hostLinearOut[2];
+  DeviceImage resolved[2];  // copiedTexture (PostProcessor.h:29): the resolved copy of a multisampled source
+  // F7 capture (takeCapture, PostProcessor.h:88 / PostProcessor.cpp:630-637)
+  bool takeCapture = false;
+  std::string captureDir, lastCapturePath;
   const void *lastSubmittedTexture = nullptr;
   ovrfsr_image lastOutput{};
   int eyeCount = 0;
@@ -128,7 +134,7 @@ int fail(ovrfsr_ctx *ctx, int status, const char *what, cudaError_t e = cudaSucc
 }
 
 void release_resources(ovrfsr_ctx *c) {
-  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); c->hostLinearIn[e].release(); c->hostLinearOut[e].release(); }
+  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); c->hostLinearIn[e].release(); c->hostLinearOut[e].release(); c->resolved[e].release(); }
   if (c->evCreated) {
     for (int i = 0; i < kQueryCount; ++i) { cudaEventDestroy(c->evStart[i]); cudaEventDestroy(c->evEnd[i]); c->evPending[i] = false; }
     c->evCreated = false;
@@ -225,6 +231,23 @@ int run_sharpen(ovrfsr_ctx *c, int eye, const PassImage &in, const PassImage &ou
   return e == cudaSuccess ? OVRFSR_OK : fail(c, OVRFSR_ERR_CUDA, "RCAS launch", e);
 }
 
+// PostProcessor::SaveTextureToFile, PostProcessor.cpp:640-657: staging copy, then the DDS writer (capture.cpp)
+int save_capture(ovrfsr_ctx *c, const ovrfsr_image &img, cudaStream_t s) {
+  const size_t rowBytes = (size_t)img.width * bytes_per_pixel(img.format);
+  std::vector<uint8_t> host(rowBytes * img.height);
+  cudaError_t e = cudaMemcpy2DAsync(host.data(), rowBytes, img.data, img.pitch, rowBytes, img.height, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(c, OVRFSR_ERR_CUDA, "capture read-back", e);
+  char name[96];
+  if (ovrfsr_capture_filename(&c->cfg, (int64_t)std::time(nullptr), name, sizeof(name)) != OVRFSR_OK)
+    return fail(c, OVRFSR_ERR_INVALID, "capture file name");
+  c->lastCapturePath = c->captureDir.empty() ? std::string(name) : c->captureDir + "/" + name;
+  const ovrfsr_image h{host.data(), img.width, img.height, (uint32_t)rowBytes, img.format, 1, 0, 0};
+  int rc = ovrfsr_dds_write(c->lastCapturePath.c_str(), &h);
+  if (rc != OVRFSR_OK) { c->lastCapturePath.clear(); return fail(c, rc, "Error taking screen capture"); }
+  return OVRFSR_OK;
+}
+
 // PostProcessor::ApplyPostProcess, PostProcessor.cpp:563-638 (binding save/restore, hotkeys and the
 // DDS capture belong to the D3D11/Win32 side and stay in the caller)
 int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_image *out, cudaStream_t s) {
@@ -232,6 +255,16 @@ int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_i
   const int slice = (src->array_slices > 1 && eye == 1) ? 1 : 0;
   PassImage in = pass_image(*src, slice);
   ovrfsr_image result = *src;
+  if (src->sample_count > 1) { // GetInputView: multisampled sources are resolved into copiedTexture first (:219-226)
+    DeviceImage &r = c->resolved[eye];
+    if ((!r.img.data || r.img.width != src->width || r.img.height != src->height || r.img.format != src->format) &&
+        !r.alloc(src->width, src->height, src->format))
+      return fail(c, OVRFSR_ERR_NOMEM, "allocating the MSAA resolve target", cudaGetLastError());
+    cudaError_t e = launch_resolve_msaa(in, (int)src->sample_count, pass_image(r.img), s);
+    if (e != cudaSuccess) return fail(c, OVRFSR_ERR_CUDA, "MSAA resolve launch", e);
+    in = pass_image(r.img);
+    result = r.img;
+  }
   int q = -1;
   if (c->evCreated) {
     harvest_queries(c);
@@ -253,13 +286,19 @@ int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_i
   }
   if (q >= 0) { cudaEventRecord(c->evEnd[q], s); c->evPending[q] = true; }
   *out = result;
+  if (c->takeCapture && eye == 0) { // PostProcessor.cpp:634-637
+    c->takeCapture = false;
+    int rc = save_capture(c, result, s);
+    if (rc != OVRFSR_OK) return rc;
+  }
   return OVRFSR_OK;
 }
 
 int validate_image(const ovrfsr_image *im) {
   if (!im || !im->data || im->width == 0 || im->height == 0) return OVRFSR_ERR_INVALID;
   if (!valid_format(im->format)) return OVRFSR_ERR_UNSUPPORTED;
-  if (im->pitch < im->width * bytes_per_pixel(im->format) || (im->pitch % bytes_per_pixel(im->format)) != 0)
+  const uint64_t rowEntries = (uint64_t)im->width * (im->sample_count > 1 ? im->sample_count : 1u);
+  if (im->sample_count > 32 || im->pitch < rowEntries * bytes_per_pixel(im->format) || (im->pitch % bytes_per_pixel(im->format)) != 0)
     return OVRFSR_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(im->data) % bytes_per_pixel(im->format)) != 0) return OVRFSR_ERR_INVALID;
   return OVRFSR_OK;
@@ -373,6 +412,7 @@ int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, in
   int rc = validate_image(src_host);
   if (rc != OVRFSR_OK) return fail(ctx, rc, "invalid host source image");
   if ((rc = validate_image(dst_host)) != OVRFSR_OK) return fail(ctx, rc, "invalid host destination image");
+  if (src_host->sample_count > 1 || dst_host->sample_count > 1) return fail(ctx, OVRFSR_ERR_UNSUPPORTED, "multisampled host images");
   if ((rc = select_device(ctx)) != OVRFSR_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceImage &st = ctx->hostStage[eye];
@@ -409,11 +449,30 @@ int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, in
   return e == cudaSuccess ? OVRFSR_OK : fail(ctx, OVRFSR_ERR_CUDA, "device->host copy", e);
 }
 
+int ovrfsr_request_capture(ovrfsr_ctx *ctx, const char *directory) {
+  if (!ctx) return OVRFSR_ERR_INVALID;
+  ctx->captureDir = directory ? directory : "";
+  ctx->takeCapture = true; // the hotkey sets the flag, the next left-eye frame is saved (PostProcessor.cpp:699-702,634)
+  return OVRFSR_OK;
+}
+
+const char *ovrfsr_last_capture_path(const ovrfsr_ctx *ctx) { return ctx ? ctx->lastCapturePath.c_str() : ""; }
+
+int ovrfsr_resolve_msaa(const ovrfsr_image *src, const ovrfsr_image *dst, void *stream) {
+  int rc = validate_image(src);
+  if (rc != OVRFSR_OK || (rc = validate_image(dst)) != OVRFSR_OK) return rc;
+  if (src->sample_count < 2 || dst->sample_count > 1 || src->format != dst->format || src->width != dst->width || src->height != dst->height)
+    return OVRFSR_ERR_INVALID;
+  cudaError_t e = launch_resolve_msaa(pass_image(*src), (int)src->sample_count, pass_image(*dst), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? OVRFSR_OK : (e == cudaErrorInvalidValue ? OVRFSR_ERR_UNSUPPORTED : OVRFSR_ERR_CUDA);
+}
+
 // ---- stateless dispatches ---------------------------------------------------------------------
 static int check_pair(const ovrfsr_image *src, const ovrfsr_image *dst) {
   int rc = validate_image(src);
   if (rc != OVRFSR_OK) return rc;
   if ((rc = validate_image(dst)) != OVRFSR_OK) return rc;
+  if (src->sample_count > 1 || dst->sample_count > 1) return OVRFSR_ERR_UNSUPPORTED; /* resolve first (ovrfsr_resolve_msaa / ovrfsr_apply) */
   if (dst->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED; /* outputs are RGBA8 / RGB10A2 (reference) or float */
   if ((dst->format == OVRFSR_FORMAT_RGB10A2) != (src->format == OVRFSR_FORMAT_RGB10A2) && dst->format != OVRFSR_FORMAT_RGBA16F &&
       dst->format != OVRFSR_FORMAT_RGBA32F)

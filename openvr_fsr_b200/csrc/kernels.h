@@ -25,6 +25,10 @@ cudaError_t launch_nis_sharpen_strict(const PassImage &src, const PassImage &dst
 // exhaustive device check of strict RCAS's UNORM8 reciprocal: result = {mismatches, operands checked}
 cudaError_t selftest_rcas_rcp(uint32_t result[2], cudaStream_t s);
 
+// MSAA resolve front-end (GetInputView's ResolveSubresource, PostProcessor.cpp:219-226): dst = mean over the
+// `samples` consecutive samples of each texel; same format both sides.  One arithmetic (strict) for both math modes.
+cudaError_t launch_resolve_msaa(const PassImage &srcSamples, int samples, const PassImage &dst, cudaStream_t s);
+
 // bumped once per kernel launch by every launcher (ovrfsr_kernel_launches)
 void count_launch();
 

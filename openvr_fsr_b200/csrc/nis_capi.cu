@@ -42,7 +42,7 @@ inline uint32_t bpp(int fmt) { return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt 
 int check(const ovrfsr_image *im, bool isDst) {
   if (!im || !im->data || im->width == 0 || im->height == 0) return OVRFSR_ERR_INVALID;
   if (im->format < OVRFSR_FORMAT_RGBA8 || im->format > OVRFSR_FORMAT_RGB10A2) return OVRFSR_ERR_UNSUPPORTED;
-  if (isDst && im->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED;
+  if ((isDst && im->format == OVRFSR_FORMAT_BGRA8) || im->sample_count > 1) return OVRFSR_ERR_UNSUPPORTED;
   if (im->pitch < im->width * bpp(im->format) || im->pitch % bpp(im->format) ||
       reinterpret_cast<uintptr_t>(im->data) % bpp(im->format)) return OVRFSR_ERR_INVALID;
   return OVRFSR_OK;

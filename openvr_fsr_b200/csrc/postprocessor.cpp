@@ -4,6 +4,7 @@
 #include "postprocessor.h"
 
 #include <cmath>
+#include <cstdio>
 #include <iostream>
 
 Config &Config::Instance() {
@@ -66,6 +67,10 @@ void PostProcessor::Apply(EVREye eEye, const Texture_t *pTexture, const VRTextur
     initialized = true;
   }
 
+  if (takeCapture) {
+    takeCapture = false;
+    ovrfsr_request_capture(ctx, captureDir);
+  }
   const int onlyOneEye = std::abs(pBounds->uMax - pBounds->uMin) > .5f;
   const int eye = eEye == Eye_Right ? 1 : 0;
   ovrfsr_image out{};
@@ -88,6 +93,11 @@ void PostProcessor::Reset() {
   initialized = false;
   if (ctx) ovrfsr_reset(ctx);
   outputImage[0] = outputImage[1] = ovrfsr_image{};
+}
+
+void PostProcessor::TakeCapture(const char *directory) {
+  std::snprintf(captureDir, sizeof(captureDir), "%s", directory ? directory : "");
+  takeCapture = true;
 }
 
 bool PostProcessor::GetAverageGpuTimeMs(float *ms) { return ctx && ovrfsr_get_gpu_time_ms(ctx, ms) > 0; }

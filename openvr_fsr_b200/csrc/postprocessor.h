@@ -32,6 +32,9 @@ public:
   void SetStream(void *cudaStream) { stream = cudaStream; }
   // mean GPU ms per frame in debugMode ("Average GPU processing time for upscale", PostProcessor.cpp:619-626)
   bool GetAverageGpuTimeMs(float *ms);
+  // what the F7 hotkey does (`takeCapture = true`, PostProcessor.cpp:699-702): the next left-eye Apply writes its
+  // output as capture_<time>_<fsr|nis>_s<..>_r<..>.dds into `directory` (the reference uses the DLL's directory)
+  void TakeCapture(const char *directory);
 
 private:
   bool enabled = true;
@@ -40,6 +43,8 @@ private:
   ovrfsr_ctx *ctx = nullptr;
   void *stream = nullptr;
   ovrfsr_image outputImage[2] = {};
+  bool takeCapture = false;
+  char captureDir[512] = {};
 };
 
 } // namespace vr

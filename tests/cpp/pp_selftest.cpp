@@ -1,6 +1,6 @@
 // pp_selftest.cpp -- drives the C++ drop-in (vr::PostProcessor + Config singleton) exactly like the Submit detour
 // does (/root/reference/src/postprocess/VrHooks.cpp:50-62): build a Texture_t, call Apply, read the swapped handle.
-// usage: pp_selftest <in.rgba> <w> <h> <renderScale> <sharpness> <radius> <useNis> <out_left.rgba> <out_right.rgba>
+// usage: pp_selftest <in.rgba> <w> <h> <renderScale> <sharpness> <radius> <useNis> <out_left.rgba> <out_right.rgba> [captureDir]
 // Built and run by tests/test_gpu_cpp_dropin.py (nvcc, links the in-tree libovrfsr.so).
 #include <cstdio>
 #include <cstdlib>
@@ -14,7 +14,7 @@
 static int fail(const char *what) { std::fprintf(stderr, "pp_selftest: %s\n", what); return 1; }
 
 int main(int argc, char **argv) {
-  if (argc != 10) return fail("bad arguments");
+  if (argc != 10 && argc != 11) return fail("bad arguments");
   const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
   std::vector<unsigned char> host((size_t)w * h * 4);
   FILE *f = std::fopen(argv[1], "rb");
@@ -79,6 +79,14 @@ int main(int argc, char **argv) {
       }
       t.handle = origHandle;                                          // VrHooks.cpp:60
     }
+  }
+  // 4. F7: the next left-eye frame is written as a DDS file the library can read back (PostProcessor.cpp:634-657)
+  if (argc > 10) {
+    postProcessor.TakeCapture(argv[10]);
+    vr::Texture_t t{&eye[0], vr::TextureType_OvrFsrCuda, vr::ColorSpace_Gamma};
+    postProcessor.Apply(vr::Eye_Left, &t, &bounds, vr::Submit_Default);
+    const ovrfsr_image *out = static_cast<const ovrfsr_image *>(t.handle);
+    std::printf("capture requested: %ux%u\n", out->width, out->height);
   }
   for (int e = 0; e < 2; ++e) ovrfsr_image_free(&eye[e]);
   return 0;

@@ -28,8 +28,10 @@ def test_cpp_postprocessor_matches_oracle(cuda, selftest_exe, tmp_path, use_nis,
     left, right = synth.stereo_pair("natural", iw, ih, 11)
     (tmp_path / "in.rgba").write_bytes(left.tobytes())
     outs = [tmp_path / "l.rgba", tmp_path / "r.rgba"]
+    capdir = tmp_path / "captures"
+    capdir.mkdir()
     subprocess.check_call([str(selftest_exe), str(tmp_path / "in.rgba"), str(iw), str(ih), str(scale), str(sharp),
-                           str(radius), str(use_nis), str(outs[0]), str(outs[1])])
+                           str(radius), str(use_nis), str(outs[0]), str(outs[1]), str(capdir)])
     ow, oh = po.output_size(iw, ih, scale)
     for eye, img in ((0, left), (1, right)):
         got = np.frombuffer(outs[eye].read_bytes(), dtype=np.uint8).reshape(oh, ow, 4)
@@ -41,3 +43,9 @@ def test_cpp_postprocessor_matches_oracle(cuda, selftest_exe, tmp_path, use_nis,
             mid = img if scale == 1.0 else po.easu(img, ow, oh, po.upscale_constants(eye, True, iw, ih, ow, oh, radius=radius))
             want = po.rcas(mid, sc)
         assert np.array_equal(got, want)
+        if eye == 0:  # TakeCapture(): the F7 file holds the left eye's output (PostProcessor.cpp:634-657)
+            import openvr_fsr_b200 as ovr
+            files = list(capdir.iterdir())
+            assert len(files) == 1 and files[0].name.endswith("_%s_s90_r50.dds" % ("nis" if use_nis else "fsr"))
+            cap, fmt = ovr.load_dds(files[0])
+            assert fmt == ovr.FORMAT_RGBA8 and np.array_equal(cap, want)
