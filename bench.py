@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--pool", type=int, default=8, help="distinct stereo pairs per GPU per step (pool > L2)")
     ap.add_argument("--math", default="strict", choices=["fast", "strict"],
                     help="strict = bit-identical to the reference lines end to end (headline); fast = <=1 LSB per pass")
+    ap.add_argument("--streams", type=int, default=4, choices=[1, 2, 4, 6, 8],
+                    help="1 = everything on one stream; 2 = one stream per eye; 4+ = streams/2 frames in flight, one context each")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -233,13 +235,10 @@ def main():
         # device images with a 256-byte-aligned row pitch (what cudaMallocPitch / ovrfsr_image_alloc return): the
         # TMA tile loader needs a 16-byte-aligned pitch; algorithmic bytes are counted without the padding
         pool.append((ovr.to_image(np.roll(base_l, sh, axis=0), dev), ovr.to_image(np.roll(base_r, sh, axis=0), dev)))
-    pp = ovr.PostProcessor(cfg)
+    runner = EyeStreams(ovr, torch, cfg, dev, args.streams)
+    pp = runner.pps[0]
     assert np.array_equal(pp_consts_after_first(pp, pool[0][0]), consts["upscale"][0]), "rank constants differ from root's"
-
-    def step():
-        for left, right in pool:
-            pp.apply(ovr.EYE_LEFT, left)
-            pp.apply(ovr.EYE_RIGHT, right)
+    step, fork, join = (lambda: runner.step(pool)), runner.fork, runner.join
 
     def barrier():
         if world > 1:
@@ -256,8 +255,10 @@ def main():
     launches0 = ovr.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    fork()
     for _ in range(args.steps):
         step()
+    join()
     ev1.record()
     barrier()
     launches = ovr.kernel_launches() - launches0
@@ -298,6 +299,8 @@ def main():
                 "algorithmic_bytes_per_launch": EASU_BYTES_PER_EYE, "ms_per_launch": easu_ms,
                 "fp32_issue_frac": issue_frac(prof.get("easu_instr_per_px"), easu_ms),
                 "instr_per_output_px": prof.get("easu_instr_per_px"),
+                "timing": "ms_per_launch = this kernel alone on its stream (CUDA events); inside the step, kernels of "
+                          "the other eye / frame run concurrently, so ms_per_step is below the sum of launch times",
                 "note": "EASU is FP32-issue-bound, not HBM-bound, when the mask is off (DESIGN.md section 5): "
                         "fp32_issue_frac = executed warp-instructions/s (ncu count x live launch rate) / issue peak"}
     roofline_rcas = {"bound": "hbm", "kernel": "rcas_kernel", "achieved": rcas_gbs, "peak": peak, "unit": "GB/s",
@@ -314,16 +317,16 @@ def main():
     # ---- reference default radius beside the headline, and the other math mode
     masked = None
     if args.radius != 0.5:
-        masked = quick_value(ovr, torch, cfg, pool, max(3, args.steps // 2), radius=0.5)
+        masked = quick_value(ovr, torch, cfg, pool, max(3, args.steps // 2), args.streams, radius=0.5)
     other_mode = "fast" if args.math == "strict" else "strict"
-    other = quick_value(ovr, torch, cfg, pool, max(3, args.steps // 2),
+    other = quick_value(ovr, torch, cfg, pool, max(3, args.steps // 2), args.streams,
                         mathMode=ovr.MATH_FAST if other_mode == "fast" else ovr.MATH_STRICT)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline(args.radius)
 
-    pp.close()
+    runner.close()
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -332,6 +335,7 @@ def main():
             "config": {"workload": WORKLOAD, "radius": args.radius, "pairs_per_step_per_gpu": args.pool,
                        "math": args.math, "source_pitch": "256-byte aligned rows (TMA tile loads)", "l2": f"inputs larger than L2 ({args.pool} distinct pairs = "
                        f"{args.pool * 2 * IN_W * IN_H * 4 / 1e6:.0f} MB per GPU per step)",
+                       "streams": f"{args.streams} CUDA streams per GPU: {max(1, args.streams // 2)} frame(s) in flight, one stream per eye",
                        "parallelism": f"frames sharded {world}x, no data-path collective"},
             "hbm_gbs_whole_pass": value / world * PAIR_BYTES / 1e9,
             "hbm_frac_whole_pass": value / world * PAIR_BYTES / 1e9 / peak,
@@ -385,22 +389,60 @@ def per_kernel_times(ovr, pool, consts, math_mode, reps):
     return statistics.mean(te[skip:]), statistics.mean(tr[skip:])
 
 
-def quick_value(ovr, torch, cfg, pool, steps, **changes):
+class EyeStreams:
+    """The device-resident workload driver: n_streams // 2 PostProcessor contexts (frames in flight), one CUDA stream
+    per eye of each.  A context keeps one output set per eye, so its two eyes can run concurrently; frame i goes to
+    context i % n_ctx.  Kernels of different eyes / frames then share the SMs: a persistent EASU grid's last wave no
+    longer leaves SMs idle, and issue-bound EASU warps interleave with the other eye's RCAS warps."""
+
+    def __init__(self, ovr, torch, cfg, dev, n_streams):
+        self.main = torch.cuda.current_stream(dev)
+        self.pps = [ovr.PostProcessor(cfg) for _ in range(max(1, n_streams // 2))]
+        if n_streams == 1:
+            self.streams = [[self.main, self.main]]
+        else:
+            self.streams = [[torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] for _ in self.pps]
+
+    def step(self, pool):
+        n = len(self.pps)
+        for i, (left, right) in enumerate(pool):
+            self.pps[i % n].apply(0, left, stream=self.streams[i % n][0])
+            self.pps[i % n].apply(1, right, stream=self.streams[i % n][1])
+
+    def fork(self):
+        for pair in self.streams:
+            for s in pair:
+                if s is not self.main:
+                    s.wait_stream(self.main)
+
+    def join(self):
+        for pair in self.streams:
+            for s in pair:
+                if s is not self.main:
+                    self.main.wait_stream(s)
+
+    def close(self):
+        for p in self.pps:
+            p.close()
+
+
+def quick_value(ovr, torch, cfg, pool, steps, n_streams=2, **changes):
     import dataclasses
-    pp = ovr.PostProcessor(dataclasses.replace(cfg, **changes))
+    dev = pool[0][0].device
+    r = EyeStreams(ovr, torch, dataclasses.replace(cfg, **changes), dev, n_streams)
     for _ in range(2):
-        for left, right in pool:
-            pp.apply(0, left); pp.apply(1, right)
+        r.step(pool)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    r.fork()
     for _ in range(steps):
-        for left, right in pool:
-            pp.apply(0, left); pp.apply(1, right)
+        r.step(pool)
+    r.join()
     e1.record()
     torch.cuda.synchronize()
     v = len(pool) * steps / (e0.elapsed_time(e1) * 1e-3)
-    pp.close()
+    r.close()
     return v
 
 
