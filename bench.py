@@ -341,6 +341,14 @@ def main():
             "hbm_frac_whole_pass": value / world * PAIR_BYTES / 1e9 / peak,
             "roofline": roofline, "roofline_rcas": roofline_rcas, "clocks": clocks, "gpu_launches": int(launches),
         }
+        if prof.get("easu_instr_per_px") and prof.get("rcas_instr_per_px"):
+            # the bound that actually applies to the unmasked pass: warp-instruction issue slots (4 per SM per clock)
+            wi = (prof["easu_instr_per_px"] + prof["rcas_instr_per_px"]) * OUT_W * OUT_H * 2 / 32 * (value / world)
+            out["issue_roofline_whole_step"] = {
+                "achieved": wi / 1e12, "peak": 148 * 4 * sm_clock_hz / 1e12, "unit": "T warp-instr/s",
+                "frac": wi / (148 * 4 * sm_clock_hz),
+                "note": "executed warp-instructions per pair (ncu counts in profiles/kernel_constants.json) x pairs/s, "
+                        "against 148 SMs x 4 schedulers x the SM clock sampled during the run"}
         if e2e is not None:
             out["e2e"] = e2e
         if masked is not None:
