@@ -289,11 +289,11 @@ def main():
     rcas_gbs = RCAS_BYTES_PER_EYE / (rcas_ms * 1e-3) / 1e9
     prof_all = _profile_constants()
     prof = {k[: -len(args.math) - 1]: v for k, v in prof_all.items() if k.endswith("_" + args.math)}
-    sm_clock_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    sm_clock_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     def issue_frac(instr_per_px, ms):  # executed warp-instructions / s against 4 issue slots / SM / clock
         if not instr_per_px:
             return None
-        return instr_per_px * OUT_W * OUT_H / 32 / (ms * 1e-3) / (148 * 4 * sm_clock_hz * 1e6)
+        return instr_per_px * OUT_W * OUT_H / 32 / (ms * 1e-3) / (148 * 4 * sm_clock_mhz * 1e6)
     roofline = {"bound": "hbm", "kernel": "easu_kernel", "achieved": easu_gbs, "peak": peak, "unit": "GB/s",
                 "frac": easu_gbs / peak, "traffic": prof.get("easu_traffic_bytes"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": EASU_BYTES_PER_EYE, "ms_per_launch": easu_ms,
@@ -345,8 +345,8 @@ def main():
             # the bound that actually applies to the unmasked pass: warp-instruction issue slots (4 per SM per clock)
             wi = (prof["easu_instr_per_px"] + prof["rcas_instr_per_px"]) * OUT_W * OUT_H * 2 / 32 * (value / world)
             out["issue_roofline_whole_step"] = {
-                "achieved": wi / 1e12, "peak": 148 * 4 * sm_clock_hz / 1e12, "unit": "T warp-instr/s",
-                "frac": wi / (148 * 4 * sm_clock_hz),
+                "achieved": wi / 1e12, "peak": 148 * 4 * sm_clock_mhz * 1e6 / 1e12, "unit": "T warp-instr/s",
+                "frac": wi / (148 * 4 * sm_clock_mhz * 1e6),
                 "note": "executed warp-instructions per pair (ncu counts in profiles/kernel_constants.json) x pairs/s, "
                         "against 148 SMs x 4 schedulers x the SM clock sampled during the run"}
         if e2e is not None:
