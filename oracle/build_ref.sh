@@ -11,6 +11,8 @@
 #   consts_ref.cpp : ffx_a.h + ffx_fsr1.h + NIS_Config.h under A_CPU, as shipped
 #   fsr_ref.cpp    : ffx_fsr1.h:239-437 (EASU), :684-769 (RCAS), ffx_a.h:1843-1845, behind an HLSL type shim
 #   nis_ref_{scaler,sharpen}.cpp : NIS_Scaler.h verbatim (NIS_SCALER=1 / 0) behind an HLSL type shim
+#   cas_consts_ref.cpp : src/cas/ffx_a.h + ffx_cas.h under A_CPU, as shipped (CasSetup)
+#   cas_ref.cpp    : src/cas/ffx_cas.h:409-893 (CasFilter), src/cas/ffx_a.h:1455-1457, behind the same type shim
 # The reference's own build system (Visual Studio + fxc, src/CMakeLists.txt:155-170) is not run.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -43,8 +45,16 @@ NIS="$REF/src/nis/NIS_Scaler.h"
 grep -q '^#define NIS_SCALE_FLOAT 255.0$' "$NIS" || { echo "NIS_SCALE_FLOAT anchor moved"; exit 1; }
 sed 's/^#define NIS_SCALE_FLOAT 255.0$/#define NIS_SCALE_FLOAT 255.0f/' "$NIS" > "$TMP/NIS_Scaler_cpp.h"
 
+# legacy CAS path (never dispatched by the mod)
+CAS="$REF/src/cas/ffx_cas.h"; CASA="$REF/src/cas/ffx_a.h"
+sed -n '409p' "$CAS" | grep -q 'void CasFilter('      || { echo "CAS anchor 409 moved"; exit 1; }
+sed -n '893p' "$CAS" | grep -q '^ }$'                  || { echo "CAS anchor 893 moved"; exit 1; }
+sed -n '1455p' "$CASA" | grep -q 'APrxLoSqrtF1'        || { echo "CAS anchor 1455 moved"; exit 1; }
+sed -n '409,893p' "$CAS" | sed -E "$HLSL2CPP" > "$TMP/cas_lines.inc"
+sed -n '1455,1457p' "$CASA" > "$TMP/cas_prx.inc"
+
 OBJS=()
-for f in consts_ref fsr_ref nis_ref_scaler nis_ref_sharpen; do
+for f in consts_ref fsr_ref nis_ref_scaler nis_ref_sharpen cas_consts_ref cas_ref; do
   [ -f "$HERE/ref_shim/$f.cpp" ] || continue
   $CXX $CXXFLAGS -I"$REF/src" -I"$TMP" -c "$HERE/ref_shim/$f.cpp" -o "$TMP/$f.o"
   OBJS+=("$TMP/$f.o")

@@ -47,24 +47,11 @@ void ovo_fsr_easu_con(uint32_t con[16], float inVpW, float inVpH, float inW, flo
   con[14] = con[15] = 0;
 }
 
-/* ffx_a.h:482-550 AU1_AH1_AF1: table-driven float->half that TRUNCATES the
- * mantissa and clamps overflow/inf/NaN to 0x7bff.  The 2x512-entry tables are
- * regenerated here from their construction rule instead of being listed. */
-static uint32_t half_bits_trunc(float f) {
-  uint32_t u = ovo_f2u(f), i = u >> 23, e = i & 0xffu, sign = (i & 0x100u) ? 0x8000u : 0u;
-  uint32_t base, shift;
-  if (e < 103u) { base = 0; shift = 24; }
-  else if (e < 113u) { base = 0x0400u >> (113u - e); shift = 126u - e; }
-  else if (e <= 142u) { base = (e - 112u) << 10; shift = 13; }
-  else { base = 0x7bffu; shift = 24; }
-  return (base | sign) + ((u & 0x7fffffu) >> shift);
-}
-
 /* ffx_fsr1.h:662-672 */
 void ovo_fsr_rcas_con(uint32_t con[4], float sharpnessStops) {
   float s = exp2f(-sharpnessStops);
   con[0] = ovo_f2u(s);
-  con[1] = half_bits_trunc(s) + (half_bits_trunc(s) << 16); /* AU1_AH2_AF2, ffx_a.h:552 */
+  con[1] = ovo_half_bits_trunc(s) + (ovo_half_bits_trunc(s) << 16); /* AU1_AH2_AF2, ffx_a.h:552 */
   con[2] = 0;
   con[3] = 0;
 }

@@ -61,6 +61,19 @@ static inline uint16_t ovo_float_to_half(float f) {
   return (uint16_t)(s | r);
 }
 
+/* ffx_a.h:482-550 AU1_AH1_AF1: table-driven float->half that TRUNCATES the
+ * mantissa and clamps overflow/inf/NaN to 0x7bff.  The 2x512-entry tables are
+ * regenerated here from their construction rule instead of being listed. */
+static inline uint32_t ovo_half_bits_trunc(float f) {
+  uint32_t u = ovo_f2u(f), i = u >> 23, e = i & 0xffu, sign = (i & 0x100u) ? 0x8000u : 0u;
+  uint32_t base, shift;
+  if (e < 103u) { base = 0; shift = 24; }
+  else if (e < 113u) { base = 0x0400u >> (113u - e); shift = 126u - e; }
+  else if (e <= 142u) { base = (e - 112u) << 10; shift = 13; }
+  else { base = 0x7bffu; shift = 24; }
+  return (base | sign) + ((u & 0x7fffffu) >> shift);
+}
+
 static inline int ovo_bpp(int format) { return format == OVO_FMT_RGBA32F ? 16 : (format == OVO_FMT_RGBA16F ? 8 : 4); }
 
 /* in-bounds texel fetch -> float4 (rgba) */

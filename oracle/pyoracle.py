@@ -51,6 +51,14 @@ class NISConfig(C.Structure):
         return np.frombuffer(bytes(self), dtype=np.uint32).copy()
 
 
+class CasConstants(C.Structure):
+    """cb of src/cas/cas.compute.h:1-4"""
+    _fields_ = [("const0", C.c_uint32 * 4), ("const1", C.c_uint32 * 4)]
+
+    def words(self):
+        return np.frombuffer(bytes(self), dtype=np.uint32).copy()
+
+
 assert C.sizeof(UpscaleConstants) == 96 and C.sizeof(SharpenConstants) == 48 and C.sizeof(NISConfig) == 256
 
 
@@ -108,6 +116,9 @@ def oracle_lib():
             lib.ovo_nis_coef_usm.restype = f32p
         lib.ovo_group_inside.argtypes = [C.c_uint32] * 4 + [u32p, C.c_uint32]
         lib.ovo_group_inside.restype = C.c_int
+        lib.ovo_cas_setup.argtypes = [C.POINTER(CasConstants)] + [C.c_float] * 6
+        lib.ovo_cas.argtypes = [_PI, _PI, C.POINTER(CasConstants), C.c_int, C.c_int]
+        lib.ovo_cas.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -132,6 +143,9 @@ def ref_lib():
         lib.ref_NVSharpenUpdateConfig.argtypes = [C.c_void_p, C.c_float] + [C.c_uint32] * 2
         lib.ref_coef_scale.restype = f32p
         lib.ref_coef_usm.restype = f32p
+        lib.ref_cas_setup.argtypes = [u32p, u32p] + [C.c_float] * 6
+        lib.ref_cas.argtypes = [_PI, _PI, C.POINTER(CasConstants), C.c_int, C.c_int]
+        lib.ref_cas.restype = C.c_int
         _ref = lib
     return _ref
 
@@ -220,3 +234,25 @@ def nis_scaler(src, out_w, out_h, cfg, which="oracle", out_dtype=np.uint8, nthre
 def nis_sharpen(src, cfg, which="oracle", out_dtype=np.uint8, nthreads=1, src_fmt=None, dst_fmt=None):
     return _run(getattr(_lib(which), _pfx(which) + "nis_sharpen"), src, src.shape[:2], cfg, out_dtype, nthreads,
                 src_fmt, dst_fmt)
+
+
+# ---- legacy CAS path (src/cas) ---------------------------------------------------------------------------
+def cas_setup(sharpness, max_color_delta, in_w, in_h, out_w, out_h, which="oracle") -> CasConstants:
+    """CasSetup, src/cas/ffx_cas.h:375-397"""
+    c = CasConstants()
+    if which == "ref":
+        ref_lib().ref_cas_setup(c.const0, c.const1, sharpness, max_color_delta, in_w, in_h, out_w, out_h)
+    else:
+        oracle_lib().ovo_cas_setup(C.byref(c), sharpness, max_color_delta, in_w, in_h, out_w, out_h)
+    return c
+
+
+def cas(src, out_w, out_h, consts, sharpen_only, which="oracle", out_dtype=np.uint8, nthreads=1, src_fmt=None, dst_fmt=None):
+    """cas.sharpen.hlsl (sharpen_only) / cas.upscale.hlsl over the whole output, src/cas/cas.compute.h:25-47"""
+    dst = np.zeros((out_h, out_w, 4), dtype=out_dtype)
+    s, d = as_image(src, src_fmt), as_image(dst, dst_fmt)
+    fn = ref_lib().ref_cas if which == "ref" else oracle_lib().ovo_cas
+    rc = fn(C.byref(s), C.byref(d), C.byref(consts), int(bool(sharpen_only)), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"CAS oracle pass failed rc={rc}")
+    return dst
