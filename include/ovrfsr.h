@@ -207,6 +207,15 @@ OVRFSR_API float ovrfsr_mip_lod_bias(uint32_t input_width, uint32_t output_width
  * samplers without a bias of their own that filter anisotropically. */
 OVRFSR_API float ovrfsr_sampler_lod_bias(float sampler_mip_lod_bias, uint32_t sampler_max_anisotropy, float mip_lod_bias);
 
+/* The legacy CAS shaders the reference keeps under src/cas but never dispatches (src/CMakeLists.txt builds only fsr/
+ * and nis/): CasSetup (src/cas/ffx_cas.h:375-397; consts = const0[4], const1[4]) and one CasFilter per output pixel,
+ * alpha 1 (src/cas/cas.compute.h:25-47).  sharpen_only = cas.sharpen.hlsl (CAS_BETTER_DIAGONALS; dst size == src
+ * size), else cas.upscale.hlsl (dst at least as large as src).  No radius mask exists on this path. */
+OVRFSR_API void ovrfsr_cas_setup(uint32_t consts[8], float sharpness, float max_color_delta, float in_w, float in_h,
+                                 float out_w, float out_h);
+OVRFSR_API int ovrfsr_dispatch_cas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[8],
+                                   int sharpen_only, int math_mode, void *stream);
+
 /* F7 capture (PostProcessor.cpp:630-657): the next apply for the LEFT eye writes its output image to
  * <directory>/capture_<YYYYmmdd_HHMMSS>_<fsr|nis>_s<sharpness*100>_r<radius*100>.dds and clears the request.
  * That apply synchronises the stream (the reference's SaveDDSTextureToFile maps a staging copy). */

@@ -59,6 +59,8 @@ SYMBOLS = {
     "ovrfsr_version": (C.c_uint32, []),
     "ovrfsr_image_alloc": (C.c_int, [_imgp, C.c_uint32, C.c_uint32, C.c_int32]),
     "ovrfsr_image_free": (None, [_imgp]),
+    "ovrfsr_cas_setup": (None, [_u32p] + [C.c_float] * 6),
+    "ovrfsr_dispatch_cas": (C.c_int, [_imgp, _imgp, _u32p, C.c_int, C.c_int, _vp]),
     "ovrfsr_resolve_msaa": (C.c_int, [_imgp, _imgp, _vp]),
     "ovrfsr_recommended_render_size": (None, [_cfgp, _u32p, _u32p]),
     "ovrfsr_mip_lod_bias": (C.c_float, [C.c_uint32, C.c_uint32]),

@@ -233,6 +233,22 @@ def nis_sharpen(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src
     return _dispatch(L.lib().ovrfsr_dispatch_nis_sharpen, src, dst, C.cast(buf, C.c_void_p), math_mode, stream, src_fmt, dst_fmt)
 
 
+def cas_setup(sharpness, max_color_delta, in_w, in_h, out_w, out_h) -> np.ndarray:
+    """CasSetup, src/cas/ffx_cas.h:375-397: const0 and const1 as 8 words"""
+    w = (C.c_uint32 * 8)()
+    L.lib().ovrfsr_cas_setup(w, sharpness, max_color_delta, in_w, in_h, out_w, out_h)
+    return np.array(w, dtype=np.uint32)
+
+
+def cas(src, dst, consts8, sharpen_only: bool, math_mode=L.MATH_STRICT, stream=None, src_fmt=None, dst_fmt=None):
+    """The legacy CAS shaders (src/cas/cas.compute.h:25-47): sharpen in place size or adaptive upscale"""
+    c = (C.c_uint32 * 8)(*[int(x) for x in consts8])
+    s, d = image_of(src, src_fmt), image_of(dst, dst_fmt)
+    L.check(L.lib().ovrfsr_dispatch_cas(C.byref(s), C.byref(d), c, int(bool(sharpen_only)), math_mode, _stream_ptr(stream)),
+            "ovrfsr_dispatch_cas")
+    return dst
+
+
 def resolve_msaa(src_samples, dst, samples: int, stream=None, fmt=None):
     """GetInputView's ResolveSubresource (PostProcessor.cpp:219-226): (H, W*samples, 4) -> (H, W, 4) mean."""
     s, d = image_of(src_samples, fmt, samples), image_of(dst, fmt)

@@ -536,6 +536,22 @@ int ovrfsr_get_sharpen_constants(const ovrfsr_ctx *ctx, int eye, uint32_t consts
   std::memcpy(consts, ctx->sharpenConstants[ctx->textureContainsOnlyOneEye ? eye : 0], 48);
   return OVRFSR_OK;
 }
+void ovrfsr_cas_setup(uint32_t consts[8], float sharpness, float max_color_delta, float in_w, float in_h, float out_w, float out_h) {
+  if (consts) host::cas_setup(consts, sharpness, max_color_delta, in_w, in_h, out_w, out_h);
+}
+
+int ovrfsr_dispatch_cas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[8], int sharpen_only, int math_mode,
+                        void *stream) {
+  if (!consts) return OVRFSR_ERR_INVALID;
+  int rc = check_pair(src, dst);
+  if (rc != OVRFSR_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = math_mode == OVRFSR_MATH_STRICT ? launch_cas_strict(pass_image(*src), pass_image(*dst), consts, sharpen_only, s)
+                                                  : launch_cas_fast(pass_image(*src), pass_image(*dst), consts, sharpen_only, s);
+  if (e == cudaErrorInvalidValue) return OVRFSR_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? OVRFSR_OK : OVRFSR_ERR_CUDA;
+}
+
 int ovrfsr_selftest_rcp(uint32_t *mismatches, uint32_t *checked) {
   uint32_t r[2] = {0, 0};
   if (selftest_rcas_rcp(r, nullptr) != cudaSuccess) return OVRFSR_ERR_CUDA;

@@ -52,6 +52,20 @@ inline uint32_t half_bits_truncating(float f) {
 }
 
 // FsrRcasCon (ffx_fsr1.h:662-672)
+// CasSetup, src/cas/ffx_cas.h:375-397 with the A_CPU helpers of src/cas/ffx_a.h (ALerpF1 :302, ASatF1 :366, ARcpF1 :330)
+inline void cas_setup(uint32_t c[8], float sharpness, float maxColorDelta, float inW, float inH, float outW, float outH) {
+  c[0] = bits(inW * (1.0f / outW));
+  c[1] = bits(inH * (1.0f / outH));
+  c[2] = bits(0.5f * inW * (1.0f / outW) - 0.5f);
+  c[3] = bits(0.5f * inH * (1.0f / outH) - 0.5f);
+  const float lo = (0.0f > sharpness) ? 0.0f : sharpness, t = (1.0f < lo) ? 1.0f : lo;
+  const float sharp = -(1.0f / (5.0f * t + (-8.0f * t + 8.0f)));
+  c[4] = bits(sharp);
+  c[5] = half_bits_truncating(sharp) + (half_bits_truncating(maxColorDelta) << 16);
+  c[6] = bits(8.0f * inW * (1.0f / outW));
+  c[7] = bits(maxColorDelta);
+}
+
 inline void fsr_rcas_con(uint32_t con[4], float stops) {
   const float s = exp2f(-stops);
   const uint32_t h = half_bits_truncating(s);

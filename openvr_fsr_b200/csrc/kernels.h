@@ -22,6 +22,10 @@ cudaError_t launch_nis_scaler_strict(const PassImage &src, const PassImage &dst,
 cudaError_t launch_nis_sharpen_fast(const PassImage &src, const PassImage &dst, const void *cfg256, const float *coef, cudaStream_t s);
 cudaError_t launch_nis_sharpen_strict(const PassImage &src, const PassImage &dst, const void *cfg256, const float *coef, cudaStream_t s);
 
+// legacy CAS (cas_kernels.cuh).  consts = const0, const1 of src/cas/cas.compute.h:1-4 as CasSetup fills them.
+cudaError_t launch_cas_fast(const PassImage &src, const PassImage &dst, const uint32_t consts[8], int sharpenOnly, cudaStream_t s);
+cudaError_t launch_cas_strict(const PassImage &src, const PassImage &dst, const uint32_t consts[8], int sharpenOnly, cudaStream_t s);
+
 // exhaustive device check of strict RCAS's UNORM8 reciprocal: result = {mismatches, operands checked}
 cudaError_t selftest_rcas_rcp(uint32_t result[2], cudaStream_t s);
 

@@ -63,3 +63,12 @@ def test_cas_known_properties():
     ku = po.cas_setup(0.5, 1.0, w, h, ow, oh)
     up = po.cas(flat, ow, oh, ku, False)
     assert (up[4:-4, 4:-4, :3] == 128).all()
+
+
+@pytest.mark.parametrize("sharp", [0.0, 0.3, 0.75, 1.0, 1.7, -0.5])
+@pytest.mark.parametrize("mcd", [1.0, 0.25, 0.0])
+def test_library_cas_setup_matches_oracle(sharp, mcd):
+    """ovrfsr_cas_setup is host code: checked without a GPU."""
+    import openvr_fsr_b200 as ovr
+    for iw, ih, ow, oh in ((1683, 1869, 2244, 2492), (960, 1080, 1920, 2160), (100, 50, 100, 50)):
+        assert np.array_equal(ovr.cas_setup(sharp, mcd, iw, ih, ow, oh), po.cas_setup(sharp, mcd, iw, ih, ow, oh).words())
