@@ -38,6 +38,17 @@ for math in (ovr.MATH_STRICT, ovr.MATH_FAST):
                     f16 = ovr.alloc_image(ow, oh, torch.float16, dev)
                     ovr.fsr_rcas(out, f16, sc, math)
                     n += 1
+            # legacy CAS
+            if scale <= 1.0:
+                src = ovr.to_image(synth.natural_rgba8(iw, ih, 9), dev)
+                out = ovr.alloc_image(ow, oh, torch.uint8, dev)
+                if scale == 1.0:
+                    ovr.cas(src, out, ovr.cas_setup(0.8, 1.0, iw, ih, iw, ih), True, math)
+                    ovr.cas(torch.from_numpy(synth.natural_rgba8(iw, ih, 10)).to(dev), out, ovr.cas_setup(0.8, 0.5, iw, ih, iw, ih), True, math)
+                    n += 2
+                else:
+                    ovr.cas(src, out, ovr.cas_setup(0.8, 1.0, iw, ih, ow, oh), False, math)
+                    n += 1
             # NIS
             if scale <= 1.0:
                 ncfg, _ = ovr.make_nis_config(ovr.Config(fsrEnabled=True, useNis=True, renderScale=scale, sharpness=0.7, radius=radius),
