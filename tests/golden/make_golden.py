@@ -44,9 +44,6 @@ def main():
                 proj=(.45, .52, .55, .48), debug=True)
     fsr_fixture("bgra_40x24_s13_r20", synth.natural_rgba8(40, 24, 4), 1.3, 2.0, 0.5, src_fmt=po.FMT_BGRA8)
     fsr_fixture("fp16_40x24_s075_r20_f16out", synth.natural_rgba16f(40, 24, 6), 0.75, 2.0, 0.9, out_dtype=np.float16)
-    if hasattr(po.ref_lib(), "ref_nis_scaler"):
-        import make_golden_nis
-        make_golden_nis.main()
     print("golden fixtures written to", OUT)
 
 
