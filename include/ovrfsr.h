@@ -121,7 +121,10 @@ OVRFSR_API int ovrfsr_get_config(const ovrfsr_ctx *ctx, ovrfsr_config *cfg);
  *   out           receives the ctx-owned output image (upscaled+sharpened); valid until the next
  *                 apply for the same eye, reset or destroy.  One output per eye (the reference
  *                 shares one between both eyes, PostProcessor.h:43,58).
- *   stream        cudaStream_t; work is enqueued asynchronously, nothing is synchronised.
+ *   stream        cudaStream_t; work is enqueued asynchronously, nothing is synchronised.  The ctx reuses its per-eye
+ *                 intermediates and outputs on every call, so successive calls for the SAME eye of one ctx must be
+ *                 ordered (same stream, or the caller's own events); the two eyes may run on different streams, and
+ *                 frames in flight beyond that take one ctx each.
  * Lazy-initialises on first call and re-initialises when src dimensions change (:136-143).
  * Pass selection: upscale iff renderScale != 1; sharpen iff !useNis || renderScale == 1 (:586-594). */
 OVRFSR_API int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src, int only_one_eye,
