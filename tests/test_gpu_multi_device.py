@@ -33,3 +33,18 @@ def test_one_eye_per_device_matches_oracle(cuda):
         again = pp.apply(0, ovr.to_image(left, torch.device("cuda", 1))).cpu().numpy()
         pp.close()
     assert np.array_equal(again, outs[0])
+    # every kernel that opts in to > 48 KB of dynamic shared memory must do so on EACH device it runs on
+    # (regression: the opt-in used to be once per process): NVScaler and the CAS upscale on device 1, after device 0
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            dv = torch.device("cuda", d)
+            src, out = ovr.to_image(left, dv), torch.zeros((oh, ow, 4), dtype=torch.uint8, device=dv)
+            ncfg, _ = po.nis_config(False, 0, True, iw, ih, ow, oh, radius=0.5, sharpness=0.9)
+            ovr.nis_scaler(src, out, bytes(ncfg), ovr.MATH_STRICT)
+            torch.cuda.synchronize(d)
+            assert np.array_equal(out.cpu().numpy(), po.nis_scaler(left, ow, oh, ncfg))
+            kc = po.cas_setup(0.9, 1.0, iw, ih, ow, oh)
+            ovr.cas(src, out, kc.words(), False, ovr.MATH_FAST)
+            ovr.cas(src, out, kc.words(), False, ovr.MATH_STRICT)
+            torch.cuda.synchronize(d)
+            assert np.array_equal(out.cpu().numpy(), po.cas(left, ow, oh, kc, False))
