@@ -248,8 +248,8 @@ int save_capture(ovrfsr_ctx *c, const ovrfsr_image &img, cudaStream_t s) {
   return OVRFSR_OK;
 }
 
-// PostProcessor::ApplyPostProcess, PostProcessor.cpp:563-638 (binding save/restore, hotkeys and the
-// DDS capture belong to the D3D11/Win32 side and stay in the caller)
+// PostProcessor::ApplyPostProcess, PostProcessor.cpp:563-638 (the D3D11 binding save/restore and the Win32 hotkey
+// polling stay in the caller; the F7 capture is served through ovrfsr_request_capture)
 int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_image *out, cudaStream_t s) {
   // GetInputView: array textures keep the right eye in slice 1 (PostProcessor.cpp:254-268)
   const int slice = (src->array_slices > 1 && eye == 1) ? 1 : 0;
