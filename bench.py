@@ -7,10 +7,17 @@ default radius 0.5 is reported beside it as `masked_r0.5`).  A "step" is one pas
 of POOL distinct stereo pairs per GPU; the input pool (POOL x 25 MB) is larger than the 126 MB L2, so no step
 re-reads inputs from L2 (config.l2: "inputs larger than L2").
 
-  value     : whole-job pairs/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  value     : whole-job pairs/s, inputs resident in HBM, CUDA-event timed, max over ranks.  --streams (default 4):
+              streams/2 PostProcessor contexts = frames in flight, one CUDA stream per eye of each; 1 = everything
+              strictly back to back on one stream
   e2e       : same metric through PostProcessor.apply_host with pinned HOST buffers (H2D + kernels + D2H timed)
   roofline  : dominant kernel (EASU) algorithmic bytes / its mean launch time (CUDA events on the launch
-              stream, second instrumented pass) against MEASURED_PEAKS.json hbm_gbs
+              stream, second instrumented pass, the kernel alone on its stream) against MEASURED_PEAKS.json hbm_gbs;
+              fp32_issue_frac = executed warp-instructions/s of that kernel against the SM issue peak
+  issue_roofline_whole_step : executed warp-instructions per second of the whole step (ncu counts in
+              profiles/kernel_constants.json x pairs/s) against 148 SMs x 4 schedulers x the sampled SM clock -- the
+              bound that actually applies to the unmasked pass
+  clocks    : nvidia-smi SM clock / throttle reasons sampled every 20 ms inside the timed region
   cpu_baseline : the reference's own lines (oracle/_ref, kind "reference") or the restated oracle ("port")
               on the box's host cores, one stereo pair, rank 0 at N=1 only
   --impl reference : the CPU reference arm (same metric/config), rank 0 only under torchrun
