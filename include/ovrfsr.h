@@ -183,6 +183,10 @@ OVRFSR_API int ovrfsr_get_sharpen_constants(const ovrfsr_ctx *ctx, int eye, uint
  * reciprocal operands then come from a set of 512 values); this runs both over the whole set on the current device.
  * *mismatches must come back 0. */
 OVRFSR_API int ovrfsr_selftest_rcp(uint32_t *mismatches, uint32_t *checked);
+/* Device self-test: strict-math NVScaler / NVSharpen with a UNORM source evaluate GetEdgeMap's and CalcLTI's quotients
+ * (NIS_Scaler.h:244-247,373) with the in-range form of IEEE division (no exponent-range fallback); this compares it
+ * with div.rn on ~19 M pseudo-random operand pairs of that range on the current device.  *mismatches must be 0. */
+OVRFSR_API int ovrfsr_selftest_div(uint32_t *mismatches, uint32_t *checked);
 /* kernels launched by this library in this process since load (bench.py's gpu_launches) */
 OVRFSR_API uint64_t ovrfsr_kernel_launches(void);
 /* debugMode profiling (PostProcessor.cpp:547-557,601-628): mean GPU ms per apply over the samples

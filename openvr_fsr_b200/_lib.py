@@ -52,6 +52,7 @@ SYMBOLS = {
     "ovrfsr_get_upscale_constants": (C.c_int, [_vp, C.c_int, _u32p]),
     "ovrfsr_get_sharpen_constants": (C.c_int, [_vp, C.c_int, _u32p]),
     "ovrfsr_selftest_rcp": (C.c_int, [_u32p, _u32p]),
+    "ovrfsr_selftest_div": (C.c_int, [_u32p, _u32p]),
     "ovrfsr_kernel_launches": (C.c_uint64, []),
     "ovrfsr_get_gpu_time_ms": (C.c_int, [_vp, _f32p]),
     "ovrfsr_last_error": (C.c_char_p, [_vp]),

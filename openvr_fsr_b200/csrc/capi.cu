@@ -559,6 +559,13 @@ int ovrfsr_selftest_rcp(uint32_t *mismatches, uint32_t *checked) {
   if (checked) *checked = r[1];
   return OVRFSR_OK;
 }
+int ovrfsr_selftest_div(uint32_t *mismatches, uint32_t *checked) {
+  uint32_t r[2] = {0, 0};
+  if (selftest_nis_div(r, nullptr) != cudaSuccess) return OVRFSR_ERR_CUDA;
+  if (mismatches) *mismatches = r[0];
+  if (checked) *checked = r[1];
+  return OVRFSR_OK;
+}
 uint64_t ovrfsr_kernel_launches(void) { return ovrfsr::g_launches.load(std::memory_order_relaxed); }
 
 int ovrfsr_get_gpu_time_ms(ovrfsr_ctx *ctx, float *mean_ms) {

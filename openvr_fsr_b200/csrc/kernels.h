@@ -28,6 +28,8 @@ cudaError_t launch_cas_strict(const PassImage &src, const PassImage &dst, const 
 
 // exhaustive device check of strict RCAS's UNORM8 reciprocal: result = {mismatches, operands checked}
 cudaError_t selftest_rcas_rcp(uint32_t result[2], cudaStream_t s);
+// strict NIS's in-range IEEE quotient (div_rn_inrange) against div.rn on ~19 M operand pairs: {mismatches, checked}
+cudaError_t selftest_nis_div(uint32_t result[2], cudaStream_t s);
 
 // MSAA resolve front-end (GetInputView's ResolveSubresource, PostProcessor.cpp:219-226): dst = mean over the
 // `samples` consecutive samples of each texel; same format both sides.  One arithmetic (strict) for both math modes.

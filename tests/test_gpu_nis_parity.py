@@ -82,3 +82,13 @@ def test_postprocessor_nis_paths(cuda):
             want = po.nis_sharpen(img, cfg) if scale == 1.0 else po.nis_scaler(img, ow, oh, cfg)
             assert np.array_equal(got, want)
         pp.close()
+
+
+def test_strict_nis_inrange_division_equals_div_rn(cuda):
+    """Strict NIS divides with the range-check-free IEEE sequence when the source is UNORM; device check against
+    div.rn over pseudo-random operands of the ranges that path can produce."""
+    import ctypes as C
+    from openvr_fsr_b200 import _lib as L
+    bad, n = C.c_uint32(99), C.c_uint32(0)
+    L.check(L.lib().ovrfsr_selftest_div(C.byref(bad), C.byref(n)))
+    assert n.value == 2 * 64 * 148 * 4 * 256 and bad.value == 0
