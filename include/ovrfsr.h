@@ -95,8 +95,18 @@ typedef struct ovrfsr_config {
   int32_t device;         /* CUDA device ordinal, -1 = current device */
   int32_t output_format;  /* ovrfsr_format, AUTO = reference behaviour */
   int32_t math_mode;      /* ovrfsr_math */
-  int32_t reserved[5];
+  int32_t flags;          /* OVRFSR_FLAG_* bits; 0 = defaults */
+  int32_t reserved[4];
 } ovrfsr_config;
+
+/* ovrfsr_config::flags */
+/* Run EASU -> RCAS as ONE fused kernel that keeps the upscaled image in shared memory (same output bits, 79.7 -> 35.0 MB
+ * of traffic per C2 eye, one launch) whenever both passes run on the FSR path and the intermediate is UNORM (RGBA8 /
+ * RGB10A2).  Off by default: on B200 the pass is instruction-issue-bound, not traffic-bound, and the fused kernel's
+ * recomputed ring and lower occupancy make it 10-12 % SLOWER than the two dispatches (DESIGN.md section 5 has the
+ * measurements at radius 2.0, 0.5 and 0).  Default (bit clear): the reference's two dispatches (PostProcessor.cpp:586-594),
+ * with the outside-radius pixels written straight to the final image by the first one. */
+#define OVRFSR_FLAG_FUSED_FSR 1
 
 typedef struct ovrfsr_ctx ovrfsr_ctx;
 
@@ -143,6 +153,13 @@ OVRFSR_API int ovrfsr_dispatch_fsr_easu(const ovrfsr_image *src, const ovrfsr_im
 /* g_FSRSharpenShader: consts = SharpenConstants, 12 x u32 (PostProcessor.cpp:403-407) */
 OVRFSR_API int ovrfsr_dispatch_fsr_rcas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[12],
                                         int math_mode, void *stream);
+/* g_FSRUpscaleShader followed by g_FSRSharpenShader (ApplyPostProcess, PostProcessor.cpp:586-594) as ONE kernel: the
+ * upscaled image is quantised to dst->format (RGBA8, or RGB10A2 for an RGB10A2 source) exactly as the first dispatch
+ * stores it, but never leaves shared memory.  Bit-identical to the two dispatches above run back to back.  The two
+ * constant blocks must carry the same centres / radius words (they do when built by ovrfsr_make_*_constants for one
+ * eye); OVRFSR_ERR_UNSUPPORTED if this pair cannot be fused (formats, out->in scale above ~1.05). */
+OVRFSR_API int ovrfsr_dispatch_fsr_fused(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t upscale_consts[24],
+                                         const uint32_t sharpen_consts[12], int math_mode, void *stream);
 /* g_NISUpscaleShader / g_NISSharpenShader: cfg = NISConfig, 256 bytes (NIS_Config.h:37-77 + the
  * mod's centre/radius at byte 112, PostProcessor.cpp:310) */
 OVRFSR_API int ovrfsr_dispatch_nis_scaler(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256,

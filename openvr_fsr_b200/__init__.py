@@ -5,7 +5,7 @@ the C ABI (include/ovrfsr.h) and the C++ vr::PostProcessor drop-in; api.py mirro
 """
 from ._lib import (ERR_CUDA, ERR_INVALID, ERR_NOMEM, ERR_UNSUPPORTED, FORMAT_AUTO, FORMAT_BGRA8, FORMAT_RGBA8,  # noqa
                    FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGB10A2, MATH_FAST, MATH_STRICT, OK, PASSTHROUGH, OvrFsrError)
-from .api import (EYE_LEFT, EYE_RIGHT, Config, PostProcessor, TextureBounds, alloc_image, fsr_easu, fsr_rcas, image_of,  # noqa
+from .api import (EYE_LEFT, EYE_RIGHT, Config, PostProcessor, TextureBounds, alloc_image, fsr_easu, fsr_fused, fsr_rcas, image_of,  # noqa
                   kernel_launches, make_nis_config, make_sharpen_constants, make_upscale_constants, nis_scaler,
                   nis_sharpen, output_size, to_image, resolve_msaa, recommended_render_size, mip_lod_bias,
                   sampler_lod_bias, capture_filename, save_dds, load_dds, cas, cas_setup)

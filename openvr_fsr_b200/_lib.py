@@ -11,6 +11,7 @@ LIB_PATH = PKG / "libovrfsr.so"
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, PASSTHROUGH = range(6)
 FORMAT_RGBA8, FORMAT_BGRA8, FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGB10A2, FORMAT_AUTO = 0, 1, 2, 3, 4, -1
 MATH_FAST, MATH_STRICT = 0, 1
+FLAG_FUSED_FSR = 1
 
 
 class Image(C.Structure):
@@ -23,7 +24,7 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("fsr_enabled", C.c_int32), ("use_nis", C.c_int32),
                 ("render_scale", C.c_float), ("sharpness", C.c_float), ("radius", C.c_float),
                 ("debug_mode", C.c_int32), ("proj_centre", C.c_float * 4), ("device", C.c_int32),
-                ("output_format", C.c_int32), ("math_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("output_format", C.c_int32), ("math_mode", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 # every entry point include/ovrfsr.h declares: (restype, argtypes)
@@ -39,6 +40,7 @@ SYMBOLS = {
     "ovrfsr_apply_host": (C.c_int, [_vp, C.c_int, _imgp, C.c_int, _imgp, _vp]),
     "ovrfsr_dispatch_fsr_easu": (C.c_int, [_imgp, _imgp, _u32p, C.c_int, _vp]),
     "ovrfsr_dispatch_fsr_rcas": (C.c_int, [_imgp, _imgp, _u32p, C.c_int, _vp]),
+    "ovrfsr_dispatch_fsr_fused": (C.c_int, [_imgp, _imgp, _u32p, _u32p, C.c_int, _vp]),
     "ovrfsr_dispatch_nis_scaler": (C.c_int, [_imgp, _imgp, _vp, C.c_int, _vp]),
     "ovrfsr_dispatch_nis_sharpen": (C.c_int, [_imgp, _imgp, _vp, C.c_int, _vp]),
     "ovrfsr_output_size": (None, [C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p]),

@@ -28,6 +28,7 @@ class Config:
     device: int = -1
     outputFormat: int = L.FORMAT_AUTO
     mathMode: int = L.MATH_STRICT
+    fusedFsr: bool = False  # OVRFSR_FLAG_FUSED_FSR: one fused EASU->RCAS kernel instead of the two dispatches (slower on B200)
 
     def to_c(self) -> L.Config:
         c = L.Config()
@@ -37,6 +38,7 @@ class Config:
         c.debug_mode = int(self.debugMode)
         c.proj_centre = (C.c_float * 4)(*self.projCentre)
         c.device, c.output_format, c.math_mode = self.device, self.outputFormat, self.mathMode
+        c.flags = L.FLAG_FUSED_FSR if self.fusedFsr else 0
         return c
 
 
@@ -221,6 +223,16 @@ def fsr_easu(src, dst, consts24, math_mode=L.MATH_FAST, stream=None, src_fmt=Non
 def fsr_rcas(src, dst, consts12, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):
     c = (C.c_uint32 * 12)(*[int(x) for x in consts12])
     return _dispatch(L.lib().ovrfsr_dispatch_fsr_rcas, src, dst, c, math_mode, stream, src_fmt, dst_fmt)
+
+
+def fsr_fused(src, dst, consts24, consts12, math_mode=L.MATH_STRICT, stream=None, src_fmt=None, dst_fmt=None):
+    """ApplyUpscaling + ApplySharpening (FSR) as one kernel: bit-identical to fsr_easu followed by fsr_rcas."""
+    cu = (C.c_uint32 * 24)(*[int(x) for x in consts24])
+    cs = (C.c_uint32 * 12)(*[int(x) for x in consts12])
+    s, d = image_of(src, src_fmt), image_of(dst, dst_fmt)
+    L.check(L.lib().ovrfsr_dispatch_fsr_fused(C.byref(s), C.byref(d), cu, cs, math_mode, _stream_ptr(stream)),
+            "ovrfsr_dispatch_fsr_fused")
+    return dst
 
 
 def nis_scaler(src, dst, cfg256: bytes, math_mode=L.MATH_FAST, stream=None, src_fmt=None, dst_fmt=None):

@@ -151,6 +151,10 @@ int select_device(ovrfsr_ctx *c) {
 
 bool upscale_pass(const ovrfsr_config &cfg) { return cfg.render_scale != 1.f; }                    // PostProcessor.cpp:586
 bool sharpen_pass(const ovrfsr_config &cfg) { return !cfg.use_nis || cfg.render_scale == 1.f; }    // PostProcessor.cpp:591
+// both FSR passes run and the caller opted into the fused kernel (the intermediate is then never materialised)
+bool fused_pass(const ovrfsr_config &cfg) {
+  return !cfg.use_nis && upscale_pass(cfg) && sharpen_pass(cfg) && (cfg.flags & OVRFSR_FLAG_FUSED_FSR);
+}
 
 // PostProcessor::PrepareResources, PostProcessor.cpp:498-561
 int prepare_resources(ovrfsr_ctx *c, const ovrfsr_image *src) {
@@ -177,7 +181,10 @@ int prepare_resources(ovrfsr_ctx *c, const ovrfsr_image *src) {
                            c->outputHeight);
     ovrfsr_make_nis_config(c->nisSharpenConfig[e], &c->cfg, 1, e, one, c->inputWidth, c->inputHeight, c->outputWidth,
                            c->outputHeight);
-    if (upscale_pass(c->cfg) && !c->upscaled[e].alloc(c->outputWidth, c->outputHeight, c->outFormat))
+    // the upscaled image only exists when the two dispatches run (the fused kernel keeps it in shared memory; if a
+    // shape turns out not to be fusable it is allocated on first use)
+    const bool wantMid = upscale_pass(c->cfg) && !(fused_pass(c->cfg) && (c->outFormat == OVRFSR_FORMAT_RGBA8 || c->outFormat == OVRFSR_FORMAT_RGB10A2));
+    if (wantMid && !c->upscaled[e].alloc(c->outputWidth, c->outputHeight, c->outFormat))
       return fail(c, OVRFSR_ERR_NOMEM, "allocating upscaled texture", cudaGetLastError());
     if (sharpen_pass(c->cfg) && !c->sharpened[e].alloc(c->outputWidth, c->outputHeight, c->outFormat))
       return fail(c, OVRFSR_ERR_NOMEM, "allocating sharpened texture", cudaGetLastError());
@@ -205,6 +212,13 @@ void harvest_queries(ovrfsr_ctx *c) {
   }
 }
 
+// EASU followed by RCAS in one apply with a UNORM target: EASU writes the outside-radius groups straight to the final
+// image and RCAS only visits what is inside the radius (kernels.h)
+bool paired_passes(const ovrfsr_ctx *c) {
+  return !c->cfg.use_nis && upscale_pass(c->cfg) && sharpen_pass(c->cfg) &&
+         (c->outFormat == OVRFSR_FORMAT_RGBA8 || c->outFormat == OVRFSR_FORMAT_RGB10A2);
+}
+
 int run_upscale(ovrfsr_ctx *c, int eye, const PassImage &in, const PassImage &out, cudaStream_t s) {
   const bool strict = c->cfg.math_mode == OVRFSR_MATH_STRICT;
   cudaError_t e;
@@ -214,7 +228,11 @@ int run_upscale(ovrfsr_ctx *c, int eye, const PassImage &in, const PassImage &ou
     int rc = ovrfsr_dispatch_nis_scaler(&si, &di, c->nisScalerConfig[eye], c->cfg.math_mode, s);
     return rc == OVRFSR_OK ? rc : fail(c, rc, "NIS scaler dispatch");
   }
-  e = strict ? launch_easu_strict(in, out, c->upscaleConstants[eye], s) : launch_easu_fast(in, out, c->upscaleConstants[eye], s);
+  const PassImage fin = pass_image(c->sharpened[eye].img);
+  const PassImage *direct = paired_passes(c) ? &fin : nullptr;
+  const float tint = 1.0f - (float)c->sharpenConstants[eye][3] * 0.3f;
+  e = strict ? launch_easu_strict(in, out, c->upscaleConstants[eye], s, direct, tint)
+             : launch_easu_fast(in, out, c->upscaleConstants[eye], s, direct, tint);
   return e == cudaSuccess ? OVRFSR_OK : fail(c, OVRFSR_ERR_CUDA, "EASU launch", e);
 }
 
@@ -226,8 +244,9 @@ int run_sharpen(ovrfsr_ctx *c, int eye, const PassImage &in, const PassImage &ou
     int rc = ovrfsr_dispatch_nis_sharpen(&si, &di, c->nisSharpenConfig[eye], c->cfg.math_mode, s);
     return rc == OVRFSR_OK ? rc : fail(c, rc, "NIS sharpen dispatch");
   }
-  cudaError_t e = strict ? launch_rcas_strict(in, out, c->sharpenConstants[eye], s)
-                         : launch_rcas_fast(in, out, c->sharpenConstants[eye], s);
+  const bool skip = paired_passes(c);
+  cudaError_t e = strict ? launch_rcas_strict(in, out, c->sharpenConstants[eye], s, skip)
+                         : launch_rcas_fast(in, out, c->sharpenConstants[eye], s, skip);
   return e == cudaSuccess ? OVRFSR_OK : fail(c, OVRFSR_ERR_CUDA, "RCAS launch", e);
 }
 
@@ -273,13 +292,26 @@ int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_i
     if (c->evPending[q]) q = -1; // oldest sample still in flight: skip this frame rather than block
     else cudaEventRecord(c->evStart[q], s);
   }
-  if (upscale_pass(c->cfg)) {
+  bool fused = false;
+  if (fused_pass(c->cfg) && (c->outFormat == OVRFSR_FORMAT_RGBA8 || c->outFormat == OVRFSR_FORMAT_RGB10A2)) {
+    // ApplyUpscaling + ApplySharpening (PostProcessor.cpp:586-594) as one kernel; shapes it does not cover take the
+    // two dispatches below
+    const bool strict = c->cfg.math_mode == OVRFSR_MATH_STRICT;
+    const PassImage out2 = pass_image(c->sharpened[eye].img);
+    const cudaError_t e = strict ? launch_fsr_fused_strict(in, out2, c->upscaleConstants[eye], c->sharpenConstants[eye], s)
+                                 : launch_fsr_fused_fast(in, out2, c->upscaleConstants[eye], c->sharpenConstants[eye], s);
+    if (e == cudaSuccess) { fused = true; result = c->sharpened[eye].img; }
+    else if (e != cudaErrorInvalidValue && e != cudaErrorInvalidConfiguration) return fail(c, OVRFSR_ERR_CUDA, "fused EASU+RCAS launch", e);
+  }
+  if (!fused && upscale_pass(c->cfg)) {
+    if (!c->upscaled[eye].img.data && !c->upscaled[eye].alloc(c->outputWidth, c->outputHeight, c->outFormat))
+      return fail(c, OVRFSR_ERR_NOMEM, "allocating upscaled texture", cudaGetLastError());
     int rc = run_upscale(c, eye, in, pass_image(c->upscaled[eye].img), s);
     if (rc != OVRFSR_OK) return rc;
     in = pass_image(c->upscaled[eye].img);
     result = c->upscaled[eye].img;
   }
-  if (sharpen_pass(c->cfg)) {
+  if (!fused && sharpen_pass(c->cfg)) {
     int rc = run_sharpen(c, eye, in, pass_image(c->sharpened[eye].img), s);
     if (rc != OVRFSR_OK) return rc;
     result = c->sharpened[eye].img;
@@ -415,6 +447,10 @@ int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, in
   if (src_host->sample_count > 1 || dst_host->sample_count > 1) return fail(ctx, OVRFSR_ERR_UNSUPPORTED, "multisampled host images");
   if ((rc = select_device(ctx)) != OVRFSR_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // "Texture size changed, recreating resources" (PostProcessor.cpp:139-142) must happen BEFORE this eye is staged:
+  // the reset releases every ctx-owned image, the staging images included
+  if (ctx->initialized && (src_host->width != ctx->inputWidth || src_host->height != ctx->inputHeight || src_host->format != ctx->inFormat))
+    ovrfsr_reset(ctx);
   DeviceImage &st = ctx->hostStage[eye];
   if (!st.img.data || st.img.width != src_host->width || st.img.height != src_host->height || st.img.format != src_host->format) {
     if (!st.alloc(src_host->width, src_host->height, src_host->format))
@@ -488,6 +524,19 @@ int ovrfsr_dispatch_fsr_easu(const ovrfsr_image *src, const ovrfsr_image *dst, c
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = math_mode == OVRFSR_MATH_STRICT ? launch_easu_strict(pass_image(*src), pass_image(*dst), consts, s)
                                                   : launch_easu_fast(pass_image(*src), pass_image(*dst), consts, s);
+  if (e == cudaErrorInvalidConfiguration || e == cudaErrorInvalidValue) return OVRFSR_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? OVRFSR_OK : OVRFSR_ERR_CUDA;
+}
+
+int ovrfsr_dispatch_fsr_fused(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t upscale_consts[24],
+                              const uint32_t sharpen_consts[12], int math_mode, void *stream) {
+  if (!upscale_consts || !sharpen_consts) return OVRFSR_ERR_INVALID;
+  int rc = check_pair(src, dst);
+  if (rc != OVRFSR_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = math_mode == OVRFSR_MATH_STRICT
+                      ? launch_fsr_fused_strict(pass_image(*src), pass_image(*dst), upscale_consts, sharpen_consts, s)
+                      : launch_fsr_fused_fast(pass_image(*src), pass_image(*dst), upscale_consts, sharpen_consts, s);
   if (e == cudaErrorInvalidConfiguration || e == cudaErrorInvalidValue) return OVRFSR_ERR_UNSUPPORTED;
   return e == cudaSuccess ? OVRFSR_OK : OVRFSR_ERR_CUDA;
 }

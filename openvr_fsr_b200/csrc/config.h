@@ -16,7 +16,8 @@ struct Config {
   // not in the reference's Config: what it queries from the live runtime / picks implicitly
   float projCentre[4] = {0.5f, 0.5f, 0.5f, 0.5f}; // CalculateProjectionCenter, PostProcessor.cpp:104-121
   int cudaDevice = -1;
-  bool strictMath = false;
+  bool strictMath = true;   // bit-identical to the reference lines (the library default); false = FMA-contracted kernels, <= 1 LSB per pass
+  bool fusedFsr = false;    // OVRFSR_FLAG_FUSED_FSR: one fused EASU->RCAS kernel instead of the two dispatches
 
   // ONE instance per process, owned by libovrfsr.so (an inline function-local static would be duplicated in every
   // module that includes this header when the library is built with hidden visibility)

@@ -35,6 +35,11 @@ struct EasuArgs {
   uint32_t radiusSq;
   float radW, radH;         // (float)Radius.z, (float)Radius.w for Bilinear()
   int tileW, tileH;         // shared source tile extent in texels
+  // When RCAS follows in the same apply (ctx path only): outside-radius groups are final after this pass -- RCAS would
+  // only copy them (x the debug tint) -- so they are written straight to the final image `direct`, and to the
+  // intermediate `dst` only where an edge-adjacent group is inside the radius (RCAS reads one pixel across the edge).
+  ImageRW direct;           // ptr == nullptr: plain dispatch
+  float tintGB;             // 1 - debug*0.3 of the following RCAS pass
 };
 
 struct RcasArgs {
@@ -44,6 +49,7 @@ struct RcasArgs {
   float tintGB;             // 1 - debug*0.3 (fsr_rcas.hlsl:46)
   uint32_t centre[4];
   uint32_t radiusSq;
+  int skipOutside;          // the preceding EASU launch already wrote the outside-radius groups to dst (EasuArgs::direct)
 };
 
 // out pixel -> source position; the same instruction sequence is used for the tile origin and
@@ -315,6 +321,25 @@ __device__ __forceinline__ float4 decode_rgba(uint32_t p) {
   return make_float4(c0, c1, c2, c3);
 }
 
+// FLOAT -> intermediate UNORM -> FLOAT, the store / Load round trip of the two-dispatch form
+template <int FMID>
+__device__ __forceinline__ float4 mid_roundtrip(float r, float g, float b) {
+  if constexpr (FMID == OVRFSR_FORMAT_RGB10A2) {
+    return make_float4(unorm10(to_unorm<1023>(r)), unorm10(to_unorm<1023>(g)), unorm10(to_unorm<1023>(b)), 1.0f);
+  } else {
+    // to_unorm8 then the decode rcas_kernel applies to an RGBA8 source (decode_rgba: exact in strict math, the
+    // single-FFMA form in fast math); the code is already an integer, so 2^23 + v is one LOP3 instead of a PRMT
+    const uint32_t cr = to_unorm8(r) | 0x4B000000u, cg = to_unorm8(g) | 0x4B000000u, cb = to_unorm8(b) | 0x4B000000u;
+    if constexpr (kStrict) {
+      return make_float4(unorm8(u2f(cr) - 8388608.0f), unorm8(u2f(cg) - 8388608.0f), unorm8(u2f(cb) - 8388608.0f), 1.0f);
+    } else {
+      const float k = 1.0f / 255.0f;
+      return make_float4(__fmaf_rn(u2f(cr), k, -8388608.0f * k), __fmaf_rn(u2f(cg), k, -8388608.0f * k),
+                         __fmaf_rn(u2f(cb), k, -8388608.0f * k), 1.0f);
+    }
+  }
+}
+
 // TW  = shared tile row stride in texels (compile time, so every tap is base + immediate): 60 covers out->in
 //       scales up to 0.81 for a 64-wide output tile (60 texels incl. the 4 TMA alignment columns), 72 the rest up to 1.0.
 // TMA = the raw RGBA8 source box (tile + halo) arrives by cp.async.bulk.tensor into a double-buffered landing zone
@@ -479,12 +504,31 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
         }
       } else {
         const BilinAxis ax = easu_bilinear_axis(x, a.radW, a.src.w, tx0, cols);
+        const bool direct = a.direct.ptr != nullptr;
+        // the intermediate is still needed where RCAS of an edge-adjacent inside group reads across the group edge
+        const bool mid = !direct || group_inside(ggx * 16u - 8u, ggy * 16u + 8u, a.centre, a.radiusSq) ||
+                         group_inside(ggx * 16u + 24u, ggy * 16u + 8u, a.centre, a.radiusSq) ||
+                         group_inside(ggx * 16u + 8u, ggy * 16u - 8u, a.centre, a.radiusSq) ||
+                         group_inside(ggx * 16u + 8u, ggy * 16u + 24u, a.centre, a.radiusSq);
 #pragma unroll 2
         for (int k = 0; k < 8; ++k) {
           const int y = yFirst + 2 * k;
           if (y >= a.dst.h) break;
           const float3 c = easu_bilinear(sC, TW, ax, sRowAxis[y - oy0]);
-          store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
+          if (mid) store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
+          if constexpr (FOUT == OVRFSR_FORMAT_RGBA8 || FOUT == OVRFSR_FORMAT_RGB10A2) {
+            if (direct) {
+              uint8_t *row = a.direct.ptr + (size_t)y * a.direct.pitch;
+              if (a.tintGB == 1.0f) {
+                // RCAS's copy is the identity on UNORM codes (decode -> x1 -> encode): the same bits go to the final image
+                store_opaque<FOUT>(row, x, c.x, c.y, c.z);
+              } else {
+                // OutputTexture[p] = mul * InputTexture[p] on the stored-then-loaded value (fsr_rcas.hlsl:45-53)
+                const float4 m = mid_roundtrip<FOUT>(c.x, c.y, c.z);
+                store_texel<FOUT>(row, x, 1.0f * m.x, a.tintGB * m.y, a.tintGB * m.z, 1.0f * m.w);
+              }
+            }
+          }
         }
       }
     }
@@ -551,9 +595,42 @@ __device__ __forceinline__ float3 rcas_filter_mode(const float4 b, const float4 
   else return rcas_filter_fast(b, d, e, f, h, sharp);
 }
 
+// four adjacent output texels -> memory; one 128-bit store when the format is 4 bytes wide and alignment allows
+template <int FOUT>
+__device__ __forceinline__ void store_quad(const ImageRW &dst, bool vec, int x, int y, const float4 (&px)[4]) {
+  uint8_t *row = dst.ptr + (size_t)y * dst.pitch;
+  if constexpr (FOUT == OVRFSR_FORMAT_RGBA8 || FOUT == OVRFSR_FORMAT_RGB10A2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (FOUT == OVRFSR_FORMAT_RGBA8)
+        w[i] = __byte_perm(__byte_perm(to_unorm8(px[i].x), to_unorm8(px[i].y), 0x0040), __byte_perm(to_unorm8(px[i].z), to_unorm8(px[i].w), 0x0040), 0x5410);
+      else
+        w[i] = to_unorm<1023>(px[i].x) | (to_unorm<1023>(px[i].y) << 10) | (to_unorm<1023>(px[i].z) << 20) | (to_unorm<3>(px[i].w) << 30);
+    }
+    if (vec && x + 3 < dst.w) {
+      *reinterpret_cast<uint4 *>(row + (size_t)x * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x + i < dst.w) reinterpret_cast<uint32_t *>(row)[x + i] = w[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (x + i < dst.w) store_texel<FOUT>(row, x + i, px[i].x, px[i].y, px[i].z, px[i].w);
+  }
+}
+
 // One CTA: 64x32 output pixels; the (66 x 34) source box arrives by TMA (zero fill outside the image is exactly
 // Texture2D.Load's behaviour) and is decoded once into a float4 tile.  One warp per 16x16 group; each lane walks a
 // column of 8 rows and keeps the b / e / h texels of the cross in registers, so a pixel costs 3 shared loads, not 5.
+// One tile per CTA on purpose: at 44 registers and 46 KB four CTAs share an SM and the hardware scheduler balances the
+// 2808 tiles; a persistent variant (double-buffered landing zones, a lane owning 4 adjacent pixels for 128-bit
+// stores, 72 registers, 3 CTAs per SM) was measured at 46.8 us against this kernel's 39.1 us per C2 eye
+// (profiles/r2_rejected_experiments.md).
+// skipOutside (ctx path, EASU ran with EasuArgs::direct): outside-radius groups are already final in dst, so CTAs
+// without an inside group return at once and outside groups of mixed tiles store nothing.
 template <int FIN, int FOUT, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant__ RcasArgs a,
                                                            const __grid_constant__ CUtensorMap srcMap) {
@@ -566,6 +643,16 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
   // same UNORM layout in and out: outside-radius texels pass through bit for bit
   constexpr bool kRawCopy = FIN == FOUT && (FIN == OVRFSR_FORMAT_RGBA8 || FIN == OVRFSR_FORMAT_RGB10A2);
 
+  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
+  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
+  if (a.skipOutside) {
+    // uniform per CTA: nothing of this tile is inside the radius -> nothing to do (also no TMA load was issued yet)
+    bool any = false;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      any = any || group_inside((blockIdx.x * 4u + (g & 3)) * 16u + 8u, (blockIdx.y * 2u + (g >> 2)) * 16u + 8u, a.centre, a.radiusSq);
+    if (!any) return;
+  }
   if constexpr (TMA) {
     if (tid == 0) {
       mbar_init(&tileBar, 1);
@@ -574,8 +661,6 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       tma_load_2d(sRaw, &srcMap, ox0 - 4, sy0, &tileBar); // x origin 16-byte aligned: 3 unused texels on the left
     }
   }
-  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
-  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
 
   if constexpr (TMA) {
     // a CTA whose 8 groups are all outside the radius and copy raw bytes needs no decoded tile at all
@@ -616,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
       b = e; e = h; p += kRcasTW;
     }
-  } else {
+  } else if (!a.skipOutside) {
     // OutputTexture[p] = mul * InputTexture[p], alpha included (fsr_rcas.hlsl:45-53)
     if constexpr (TMA && kRawCopy) {
       if (a.tintGB == 1.0f) {

@@ -74,13 +74,18 @@ static inline uint32_t ovo_half_bits_trunc(float f) {
   return (base | sign) + ((u & 0x7fffffu) >> shift);
 }
 
-static inline int ovo_bpp(int format) { return format == OVO_FMT_RGBA32F ? 16 : (format == OVO_FMT_RGBA16F ? 8 : 4); }
+static inline int ovo_bpp(int format) {
+  return format == OVO_FMT_RGBA32F ? 16 : (format == OVO_FMT_RGB32F ? 12 : (format == OVO_FMT_RGBA16F ? 8 : 4));
+}
 
 /* in-bounds texel fetch -> float4 (rgba) */
 static inline void ovo_texel(const ovo_image *im, int x, int y, float o[4]) {
   const uint8_t *row = (const uint8_t *)im->data + (size_t)y * (size_t)im->pitch;
   if (im->format == OVO_FMT_RGBA32F) {
     memcpy(o, row + (size_t)x * 16, 16);
+  } else if (im->format == OVO_FMT_RGB32F) { /* a missing component reads as 1 in alpha (D3D11 default for .w) */
+    memcpy(o, row + (size_t)x * 12, 12);
+    o[3] = 1.0f;
   } else if (im->format == OVO_FMT_RGBA16F) {
     const uint16_t *p = (const uint16_t *)(row + (size_t)x * 8);
     o[0] = ovo_half_to_float(p[0]); o[1] = ovo_half_to_float(p[1]);
@@ -93,9 +98,9 @@ static inline void ovo_texel(const ovo_image *im, int x, int y, float o[4]) {
   } else {
     const uint8_t *p = row + (size_t)x * 4;
     float a = (float)p[0] / 255.0f, b = (float)p[1] / 255.0f, c = (float)p[2] / 255.0f;
-    o[3] = (float)p[3] / 255.0f;
+    o[3] = im->format == OVO_FMT_BGRX8 ? 1.0f : (float)p[3] / 255.0f; /* X8: alpha reads as 1 */
     o[1] = b;
-    if (im->format == OVO_FMT_BGRA8) { o[0] = c; o[2] = a; } else { o[0] = a; o[2] = c; }
+    if (im->format == OVO_FMT_BGRA8 || im->format == OVO_FMT_BGRX8) { o[0] = c; o[2] = a; } else { o[0] = a; o[2] = c; }
   }
 }
 

@@ -135,3 +135,22 @@ def test_apply_host_pitched_host_rows(cuda):
         assert np.array_equal(dst.numpy(), _oracle_fsr(img, eye, True, 0.75, 0.5, 0.9))
         assert bool((dbuf[:, ow * 4:] == 0xAB).all())
     pp.close()
+
+
+def test_apply_host_survives_a_size_change(cuda):
+    """'Texture size changed, recreating resources' (PostProcessor.cpp:139-142) through the host entry: the reset must
+    not free the eye that is being staged (round-1 advisor finding: the ctx disabled itself permanently)."""
+    import torch
+    import openvr_fsr_b200 as ovr
+    from openvr_fsr_b200 import synth
+    from oracle import pyoracle as po
+    pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=0.75, sharpness=0.9, radius=0.5))
+    for (w, h, seed) in ((301, 211, 8), (160, 120, 9), (301, 211, 10)):
+        img = synth.natural_rgba8(w, h, seed)
+        ow, oh = po.output_size(w, h, 0.75)
+        for eye in (0, 1):
+            src, dst = torch.from_numpy(img).pin_memory(), torch.empty((oh, ow, 4), dtype=torch.uint8).pin_memory()
+            pp.apply_host(eye, src, dst)
+            torch.cuda.synchronize()
+            assert np.array_equal(dst.numpy(), _oracle_fsr(img, eye, True, 0.75, 0.5, 0.9)), (w, h, eye)
+    pp.close()

@@ -29,4 +29,13 @@ for math, mname in ((ovr.MATH_STRICT, "strict"), (ovr.MATH_FAST, "fast")):
         torch.cuda.synchronize()
         te = statistics.mean(m[0].elapsed_time(m[1]) for m in marks[8:]) * 1e3
         tr = statistics.mean(m[1].elapsed_time(m[2]) for m in marks[8:]) * 1e3
+        fm = []
+        for rep in range(6):
+            for i in range(8):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                e[0].record(); ovr.fsr_fused(pool[i], dst, uc, sc, math); e[1].record()
+                fm.append(e)
+        torch.cuda.synchronize()
+        tf = statistics.mean(m[0].elapsed_time(m[1]) for m in fm[8:]) * 1e3
+        print(f"{mname} radius {radius}: FUSED {tf:6.1f} us ({EASU_B / tf / 1e3:6.0f} GB/s of its own {EASU_B} B)   two-pass sum {te + tr:6.1f} us")
         print(f"{mname} radius {radius}: EASU {te:6.1f} us ({EASU_B / te / 1e3:6.0f} GB/s)  RCAS {tr:6.1f} us ({RCAS_B / tr / 1e3:6.0f} GB/s)")
