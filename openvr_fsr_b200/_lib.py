@@ -5,8 +5,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libovrfsr.so"
+# OVRFSR_LIB: dev-only override used by tools/ A/B measurements against an older build of the library
+LIB_PATH = Path(os.environ["OVRFSR_LIB"]) if os.environ.get("OVRFSR_LIB") else PKG / "libovrfsr.so"
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, PASSTHROUGH = range(6)
 FORMAT_RGBA8, FORMAT_BGRA8, FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGB10A2, FORMAT_AUTO = 0, 1, 2, 3, 4, -1
@@ -88,6 +91,8 @@ def lib():
                                "(there is no CPU fallback for the CUDA path)")
         l = C.CDLL(str(LIB_PATH))
         for name, (res, args) in SYMBOLS.items():
+            if os.environ.get("OVRFSR_LIB") and not hasattr(l, name):
+                continue  # an older build under A/B measurement
             fn = getattr(l, name)  # AttributeError if the library does not export it
             fn.restype, fn.argtypes = res, args
         _lib = l

@@ -4,6 +4,7 @@
 // calls fail with OVRFSR_ERR_CUDA.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <ctime>
@@ -215,7 +216,8 @@ void harvest_queries(ovrfsr_ctx *c) {
 // EASU followed by RCAS in one apply with a UNORM target: EASU writes the outside-radius groups straight to the final
 // image and RCAS only visits what is inside the radius (kernels.h)
 bool paired_passes(const ovrfsr_ctx *c) {
-  return !c->cfg.use_nis && upscale_pass(c->cfg) && sharpen_pass(c->cfg) &&
+  static const bool off = getenv("OVRFSR_NO_PAIR") != nullptr; // dev A/B switch
+  return !off && !c->cfg.use_nis && upscale_pass(c->cfg) && sharpen_pass(c->cfg) &&
          (c->outFormat == OVRFSR_FORMAT_RGBA8 || c->outFormat == OVRFSR_FORMAT_RGB10A2);
 }
 

@@ -374,6 +374,9 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
     sy0 = (int)floorf(easu_pos(oy0, a.c0y, a.c0w)) - 1;
   };
 
+  // Static schedule t = blockIdx.x, += gridDim.x.  (Taking tiles by cluster launch control, as nis_scaler_kernel does,
+  // was measured too: 108.4 vs 106.9 us at radius 2.0 where all tiles cost the same, 56.0 vs 57.1 us at radius 0.5 --
+  // not worth the extra latency on the tile loop here; profiles/r2_rejected_experiments.md.)
   int t = blockIdx.x;
   if constexpr (TMA) {
     if (tid == 0) {
@@ -444,9 +447,9 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
     // one row term per output row of the tile for the bilinear fallback (skipped when every group is inside)
     if (tid < kTileH && oy0 + tid < a.dst.h) sRowAxis[tid] = easu_bilinear_axis(oy0 + tid, a.radH, a.src.h, sy0, th);
     const int anyInside = __syncthreads_or(inside);
+    const int tn2 = t + gridDim.x;
     if constexpr (TMA) {
       // the landing zone is fully decoded: refill it with the NEXT tile's box while this tile is filtered
-      const int tn2 = t + gridDim.x;
       if (tid == 0 && tn2 < numTiles) {
         int nox, noy, nsx, nsy;
         tile_origin(tn2, nox, noy, nsx, nsy);

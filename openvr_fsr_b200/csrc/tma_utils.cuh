@@ -46,6 +46,34 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 // order this thread's prior generic-proxy accesses to shared memory before subsequent async-proxy (TMA) ones
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ---- cluster launch control (sm_100): a running CTA cancels a not-yet-launched CTA of its own grid and takes over its
+// block index -- hardware work stealing, i.e. a persistent kernel whose work list is balanced dynamically without a
+// global counter.  try_cancel is asynchronous: the 16-byte response lands in shared memory and completes `bar`.
+__device__ __forceinline__ void clc_try_cancel(void *response16, uint64_t *bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                   smem_u32(response16)),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+// blockIdx.x of the cancelled CTA, or -1 when nothing was left to cancel (no further try_cancel may be issued then)
+__device__ __forceinline__ int clc_cancelled_block_x(const void *response16) {
+  uint32_t x, valid;
+  asm volatile(
+      "{\n"
+      ".reg .pred p1;\n"
+      ".reg .b128 r;\n"
+      "ld.shared.b128 r, [%2];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n"
+      "selp.u32 %1, 1, 0, p1;\n"
+      "mov.u32 %0, 0;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n"
+      "}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(smem_u32(response16))
+      : "memory");
+  return valid ? (int)x : -1;
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
