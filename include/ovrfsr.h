@@ -53,15 +53,29 @@ typedef enum ovrfsr_format {
   OVRFSR_FORMAT_RGB10A2 = 4, /* DXGI_FORMAT_R10G10B10A2_UNORM: one little-endian u32 per texel, R bits 0-9, G 10-19,
                                 B 20-29, A 30-31.  As an output it is only produced from an RGB10A2 source -- the case
                                 DetermineOutputFormat() exists for (:63-74) */
+  OVRFSR_FORMAT_BGRX8 = 5,   /* DXGI_FORMAT_B8G8R8X8_UNORM (:54-55): source only; the X byte reads as alpha 1 */
+  OVRFSR_FORMAT_RGB32F = 6,  /* DXGI_FORMAT_R32G32B32_FLOAT (:34-35): source only, 12 bytes per texel, alpha reads as 1;
+                                ovrfsr_apply expands it to RGBA32F first (ovrfsr_expand_rgb32f), the stateless dispatches
+                                return OVRFSR_ERR_UNSUPPORTED for it */
   OVRFSR_FORMAT_AUTO = -1    /* output only: DetermineOutputFormat(), :63-74 -> RGB10A2 for an RGB10A2 source, else RGBA8 */
 } ovrfsr_format;
+
+/* DXGI variant tags, OR-ed into ovrfsr_image::format of a SOURCE image.  The kernels view _SRGB and _TYPELESS textures as
+ * plain UNORM (MakeSrgbFormatsTypeless / TranslateTypelessFormats, PostProcessor.cpp:30-61: no sRGB decode happens on this
+ * path), so the tags change no pixel; they exist so that vr::PostProcessor can reproduce the colour-space tag the
+ * reference hands to the real Submit (inputIsSrgb, :504 with IsConsideredSrgbByOpenVR, :76-92). */
+#define OVRFSR_FORMAT_LAYOUT_MASK 0xff
+#define OVRFSR_FORMAT_SRGB_BIT 0x100     /* DXGI_FORMAT_*_UNORM_SRGB */
+#define OVRFSR_FORMAT_TYPELESS_BIT 0x200 /* DXGI_FORMAT_*_TYPELESS */
 
 /* arithmetic mode of the kernels */
 typedef enum ovrfsr_math {
   OVRFSR_MATH_FAST = 0,  /* FMA contraction + regrouped taps: each pass is <= 1 LSB (RGBA8) from the reference lines
                             on identical inputs.  Note that EASU -> RGBA8 -> RCAS amplifies a 1-LSB intermediate
                             difference in dark regions (RCAS divides by the ring maximum), as it does between any two
-                            D3D11 GPUs; use STRICT when the composed result must match to the bit. */
+                            D3D11 GPUs; use STRICT when the composed result must match to the bit.  Measured on the
+                            C2-sized test images: max 3 LSB, < 6e-6 of the channel values beyond 1 LSB (asserted <= 4
+                            LSB / 1e-4 in tests/test_gpu_fsr_parity.py). */
   OVRFSR_MATH_STRICT = 1 /* the reference's operation order, no contraction: bit-identical to the reference lines,
                             end to end.  The default of ovrfsr_config_default. */
 } ovrfsr_math;
@@ -218,6 +232,12 @@ OVRFSR_API void ovrfsr_image_free(ovrfsr_image *img);
 
 
 /* ---- the callers either side of the path -------------------------- */
+/* R32G32B32_FLOAT source (PostProcessor.cpp:34-35) -> RGBA32F with alpha 1, what a shader reads from such a view.
+ * src->format RGB32F (12-byte texels), dst->format RGBA32F, same size.  Asynchronous on `stream`. */
+OVRFSR_API int ovrfsr_expand_rgb32f(const ovrfsr_image *src, const ovrfsr_image *dst, void *stream);
+/* IsConsideredSrgbByOpenVR (PostProcessor.cpp:76-92) on a tagged ovrfsr_format: 1 for the _SRGB variants of RGBA8 /
+ * BGRA8 / BGRX8 and for the _TYPELESS variants of RGBA8 / BGRA8 / BGRX8 / RGB10A2 */
+OVRFSR_API int ovrfsr_format_considered_srgb(int32_t tagged_format);
 /* GetInputView's MSAA branch (PostProcessor.cpp:219-226, ResolveSubresource): dst[x,y] = mean of the
  * sample_count samples of texel (x,y), same format in and out; src_samples laid out as ovrfsr_image::sample_count
  * describes (its width is the texel width).  Asynchronous on `stream`. */

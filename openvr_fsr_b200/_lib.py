@@ -13,6 +13,8 @@ LIB_PATH = Path(os.environ["OVRFSR_LIB"]) if os.environ.get("OVRFSR_LIB") else P
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, PASSTHROUGH = range(6)
 FORMAT_RGBA8, FORMAT_BGRA8, FORMAT_RGBA16F, FORMAT_RGBA32F, FORMAT_RGB10A2, FORMAT_AUTO = 0, 1, 2, 3, 4, -1
+FORMAT_BGRX8, FORMAT_RGB32F = 5, 6
+FORMAT_SRGB_BIT, FORMAT_TYPELESS_BIT, FORMAT_LAYOUT_MASK = 0x100, 0x200, 0xff
 MATH_FAST, MATH_STRICT = 0, 1
 FLAG_FUSED_FSR = 1
 
@@ -68,6 +70,8 @@ SYMBOLS = {
     "ovrfsr_cas_setup": (None, [_u32p] + [C.c_float] * 6),
     "ovrfsr_dispatch_cas": (C.c_int, [_imgp, _imgp, _u32p, C.c_int, C.c_int, _vp]),
     "ovrfsr_resolve_msaa": (C.c_int, [_imgp, _imgp, _vp]),
+    "ovrfsr_expand_rgb32f": (C.c_int, [_imgp, _imgp, _vp]),
+    "ovrfsr_format_considered_srgb": (C.c_int, [C.c_int32]),
     "ovrfsr_recommended_render_size": (None, [_cfgp, _u32p, _u32p]),
     "ovrfsr_mip_lod_bias": (C.c_float, [C.c_uint32, C.c_uint32]),
     "ovrfsr_sampler_lod_bias": (C.c_float, [C.c_float, C.c_uint32, C.c_float]),

@@ -68,6 +68,11 @@ def _format_of(t) -> int:
 def image_of(t, fmt: int | None = None, samples: int = 1) -> L.Image:
     """Describe a (H, W, 4) tensor (CUDA or pinned host) as an ovrfsr_image; rows may be strided.  With
     samples > 1 the tensor is (H, W * samples, 4): the samples of one texel are consecutive (multisampled source)."""
+    if fmt is not None and (fmt & L.FORMAT_LAYOUT_MASK) == L.FORMAT_RGB32F and fmt >= 0:
+        # R32G32B32_FLOAT: (H, W, 3) float32, 12-byte texels
+        if t.dim() != 3 or t.shape[2] != 3 or t.stride(2) != 1 or t.stride(1) != 3:
+            raise ValueError("an RGB32F image is a (H, W, 3) float32 tensor with packed pixels")
+        return L.Image(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0) * t.element_size(), fmt, 1, 0, 0)
     if t.dim() != 3 or t.shape[2] != 4 or t.stride(2) != 1 or t.stride(1) != 4:
         raise ValueError("expected a (H, W, 4) tensor with packed pixels")
     if samples > 1 and t.shape[1] % samples:
@@ -266,6 +271,18 @@ def resolve_msaa(src_samples, dst, samples: int, stream=None, fmt=None):
     s, d = image_of(src_samples, fmt, samples), image_of(dst, fmt)
     L.check(L.lib().ovrfsr_resolve_msaa(C.byref(s), C.byref(d), _stream_ptr(stream)), "ovrfsr_resolve_msaa")
     return dst
+
+
+def expand_rgb32f(src, dst, stream=None):
+    """R32G32B32_FLOAT (H, W, 3) float32 -> RGBA32F (H, W, 4) with alpha 1 (PostProcessor.cpp:34-35: such a view reads 1 in .w)."""
+    s, d = image_of(src, L.FORMAT_RGB32F), image_of(dst, L.FORMAT_RGBA32F)
+    L.check(L.lib().ovrfsr_expand_rgb32f(C.byref(s), C.byref(d), _stream_ptr(stream)), "ovrfsr_expand_rgb32f")
+    return dst
+
+
+def format_considered_srgb(tagged_format: int) -> bool:
+    """IsConsideredSrgbByOpenVR, PostProcessor.cpp:76-92, on a tagged ovrfsr_format"""
+    return bool(L.lib().ovrfsr_format_considered_srgb(int(tagged_format)))
 
 
 def recommended_render_size(cfg: Config, width: int, height: int) -> tuple[int, int]:

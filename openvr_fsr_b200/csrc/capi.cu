@@ -25,8 +25,16 @@ namespace {
 
 constexpr int kQueryCount = 6; // QUERY_COUNT, PostProcessor.h:78
 
-inline uint32_t bytes_per_pixel(int fmt) { return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u); }
-inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGB10A2; }
+inline uint32_t bytes_per_pixel(int fmt) {
+  return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt == OVRFSR_FORMAT_RGB32F ? 12u : (fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u));
+}
+inline bool valid_format(int fmt) { return fmt >= OVRFSR_FORMAT_RGBA8 && fmt <= OVRFSR_FORMAT_RGB32F; }
+// the DXGI variant tags (_SRGB / _TYPELESS) change no pixel on this path: strip them at the boundary
+inline ovrfsr_image untagged(const ovrfsr_image *im) {
+  ovrfsr_image r = *im;
+  if (r.format >= 0) r.format &= OVRFSR_FORMAT_LAYOUT_MASK;
+  return r;
+}
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 struct DeviceImage {
@@ -80,6 +88,22 @@ cudaError_t repitch_rows(void *dst, size_t dpitch, const void *src, size_t spitc
   return cudaGetLastError();
 }
 
+// R32G32B32_FLOAT -> RGBA32F, alpha 1 (a three-component view reads 1 in .w)
+__global__ void __launch_bounds__(256) expand_rgb32f_kernel(float4 *__restrict__ dst, size_t dpitch, const float *__restrict__ src, size_t spitch,
+                                                            uint32_t w, uint32_t h) {
+  const uint32_t x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const float *s = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(src) + (size_t)y * spitch) + 3 * (size_t)x;
+  reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(dst) + (size_t)y * dpitch)[x] = make_float4(s[0], s[1], s[2], 1.0f);
+}
+cudaError_t expand_rgb32f(const ovrfsr_image &src, const ovrfsr_image &dst, cudaStream_t s) {
+  const dim3 grid((src.width + 255) / 256, src.height);
+  expand_rgb32f_kernel<<<grid, 256, 0, s>>>(static_cast<float4 *>(dst.data), dst.pitch, static_cast<const float *>(src.data), src.pitch,
+                                              src.width, src.height);
+  count_launch();
+  return cudaGetLastError();
+}
+
 PassImage pass_image(const ovrfsr_image &im, int slice = 0) {
   PassImage p;
   p.ptr = static_cast<uint8_t *>(im.data) + (size_t)slice * im.slice_pitch;
@@ -108,6 +132,7 @@ struct ovrfsr_ctx {
   DeviceImage hostStage[2]; // device staging of host-submitted eyes (ovrfsr_apply_host)
   DeviceBuffer hostLinearIn[2], hostLinearOut[2];
   DeviceImage resolved[2];  // copiedTexture (PostProcessor.h:29): the resolved copy of a multisampled source
+  DeviceImage expanded[2];  // RGBA32F copy of an R32G32B32_FLOAT source
   // F7 capture (takeCapture, PostProcessor.h:88 / PostProcessor.cpp:630-637)
   bool takeCapture = false;
   std::string captureDir, lastCapturePath;
@@ -135,7 +160,7 @@ int fail(ovrfsr_ctx *ctx, int status, const char *what, cudaError_t e = cudaSucc
 }
 
 void release_resources(ovrfsr_ctx *c) {
-  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); c->hostLinearIn[e].release(); c->hostLinearOut[e].release(); c->resolved[e].release(); }
+  for (int e = 0; e < 2; ++e) { c->upscaled[e].release(); c->sharpened[e].release(); c->hostStage[e].release(); c->hostLinearIn[e].release(); c->hostLinearOut[e].release(); c->resolved[e].release(); c->expanded[e].release(); }
   if (c->evCreated) {
     for (int i = 0; i < kQueryCount; ++i) { cudaEventDestroy(c->evStart[i]); cudaEventDestroy(c->evEnd[i]); c->evPending[i] = false; }
     c->evCreated = false;
@@ -286,6 +311,18 @@ int apply_post_process(ovrfsr_ctx *c, int eye, const ovrfsr_image *src, ovrfsr_i
     in = pass_image(r.img);
     result = r.img;
   }
+  if (src->format == OVRFSR_FORMAT_RGB32F) { // three-component float source: the kernels read it through an RGBA32F copy
+    if (src->sample_count > 1) return fail(c, OVRFSR_ERR_UNSUPPORTED, "multisampled R32G32B32_FLOAT source");
+    DeviceImage &x = c->expanded[eye];
+    if ((!x.img.data || x.img.width != src->width || x.img.height != src->height) && !x.alloc(src->width, src->height, OVRFSR_FORMAT_RGBA32F))
+      return fail(c, OVRFSR_ERR_NOMEM, "allocating the RGBA32F copy of an RGB32F source", cudaGetLastError());
+    ovrfsr_image sl = *src;
+    sl.data = static_cast<uint8_t *>(src->data) + (size_t)slice * src->slice_pitch;
+    cudaError_t e = expand_rgb32f(sl, x.img, s);
+    if (e != cudaSuccess) return fail(c, OVRFSR_ERR_CUDA, "RGB32F expansion launch", e);
+    in = pass_image(x.img);
+    result = x.img;
+  }
   int q = -1;
   if (c->evCreated) {
     harvest_queries(c);
@@ -332,9 +369,10 @@ int validate_image(const ovrfsr_image *im) {
   if (!im || !im->data || im->width == 0 || im->height == 0) return OVRFSR_ERR_INVALID;
   if (!valid_format(im->format)) return OVRFSR_ERR_UNSUPPORTED;
   const uint64_t rowEntries = (uint64_t)im->width * (im->sample_count > 1 ? im->sample_count : 1u);
-  if (im->sample_count > 32 || im->pitch < rowEntries * bytes_per_pixel(im->format) || (im->pitch % bytes_per_pixel(im->format)) != 0)
-    return OVRFSR_ERR_INVALID;
-  if ((reinterpret_cast<uintptr_t>(im->data) % bytes_per_pixel(im->format)) != 0) return OVRFSR_ERR_INVALID;
+  // rows and the base are aligned to the texel (to its 4-byte components for the 12-byte R32G32B32_FLOAT texel)
+  const uint32_t align = im->format == OVRFSR_FORMAT_RGB32F ? 4u : bytes_per_pixel(im->format);
+  if (im->sample_count > 32 || im->pitch < rowEntries * bytes_per_pixel(im->format) || (im->pitch % align) != 0) return OVRFSR_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(im->data) % align) != 0) return OVRFSR_ERR_INVALID;
   return OVRFSR_OK;
 }
 
@@ -408,8 +446,11 @@ int ovrfsr_get_config(const ovrfsr_ctx *ctx, ovrfsr_config *cfg) {
   return OVRFSR_OK;
 }
 
-int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src, int only_one_eye, ovrfsr_image *out, void *stream) {
+int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_tagged, int only_one_eye, ovrfsr_image *out, void *stream) {
   if (!ctx || !out || (eye != 0 && eye != 1)) return OVRFSR_ERR_INVALID;
+  ovrfsr_image src_untagged{};
+  if (src_tagged) src_untagged = untagged(src_tagged);
+  const ovrfsr_image *src = src_tagged ? &src_untagged : nullptr;
   // PostProcessor.cpp:124: disabled or unusable texture -> the frame passes through untouched
   if (!ctx->enabled || !ctx->cfg.fsr_enabled) return OVRFSR_PASSTHROUGH;
   int rc = validate_image(src);
@@ -439,9 +480,12 @@ int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src, int only_one
   return OVRFSR_OK;
 }
 
-int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, int only_one_eye,
+int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_tagged, int only_one_eye,
                       const ovrfsr_image *dst_host, void *stream) {
   if (!ctx || (eye != 0 && eye != 1)) return OVRFSR_ERR_INVALID;
+  ovrfsr_image src_untagged{};
+  if (src_tagged) src_untagged = untagged(src_tagged);
+  const ovrfsr_image *src_host = src_tagged ? &src_untagged : nullptr;
   if (!ctx->enabled || !ctx->cfg.fsr_enabled) return OVRFSR_PASSTHROUGH;
   int rc = validate_image(src_host);
   if (rc != OVRFSR_OK) return fail(ctx, rc, "invalid host source image");
@@ -497,6 +541,8 @@ int ovrfsr_request_capture(ovrfsr_ctx *ctx, const char *directory) {
 const char *ovrfsr_last_capture_path(const ovrfsr_ctx *ctx) { return ctx ? ctx->lastCapturePath.c_str() : ""; }
 
 int ovrfsr_resolve_msaa(const ovrfsr_image *src, const ovrfsr_image *dst, void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = untagged(src); src = &src_untagged_; }
   int rc = validate_image(src);
   if (rc != OVRFSR_OK || (rc = validate_image(dst)) != OVRFSR_OK) return rc;
   if (src->sample_count < 2 || dst->sample_count > 1 || src->format != dst->format || src->width != dst->width || src->height != dst->height)
@@ -505,11 +551,33 @@ int ovrfsr_resolve_msaa(const ovrfsr_image *src, const ovrfsr_image *dst, void *
   return e == cudaSuccess ? OVRFSR_OK : (e == cudaErrorInvalidValue ? OVRFSR_ERR_UNSUPPORTED : OVRFSR_ERR_CUDA);
 }
 
+int ovrfsr_expand_rgb32f(const ovrfsr_image *src, const ovrfsr_image *dst, void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = untagged(src); src = &src_untagged_; }
+  int rc = validate_image(src);
+  if (rc != OVRFSR_OK || (rc = validate_image(dst)) != OVRFSR_OK) return rc;
+  if (src->format != OVRFSR_FORMAT_RGB32F || dst->format != OVRFSR_FORMAT_RGBA32F || src->width != dst->width || src->height != dst->height ||
+      src->sample_count > 1 || dst->sample_count > 1)
+    return OVRFSR_ERR_INVALID;
+  return expand_rgb32f(*src, *dst, static_cast<cudaStream_t>(stream)) == cudaSuccess ? OVRFSR_OK : OVRFSR_ERR_CUDA;
+}
+
+int ovrfsr_format_considered_srgb(int32_t f) {
+  if (f < 0) return 0;
+  const int layout = f & OVRFSR_FORMAT_LAYOUT_MASK;
+  const bool eightBit = layout == OVRFSR_FORMAT_RGBA8 || layout == OVRFSR_FORMAT_BGRA8 || layout == OVRFSR_FORMAT_BGRX8;
+  if ((f & OVRFSR_FORMAT_SRGB_BIT) && eightBit) return 1;                                            // PostProcessor.cpp:78-81
+  if ((f & OVRFSR_FORMAT_TYPELESS_BIT) && (eightBit || layout == OVRFSR_FORMAT_RGB10A2)) return 1;  // :82-87
+  return 0;
+}
+
 // ---- stateless dispatches ---------------------------------------------------------------------
 static int check_pair(const ovrfsr_image *src, const ovrfsr_image *dst) {
   int rc = validate_image(src);
   if (rc != OVRFSR_OK) return rc;
   if ((rc = validate_image(dst)) != OVRFSR_OK) return rc;
+  if (src->format == OVRFSR_FORMAT_RGB32F) return OVRFSR_ERR_UNSUPPORTED;                                   /* expand first (ovrfsr_expand_rgb32f / ovrfsr_apply) */
+  if (dst->format == OVRFSR_FORMAT_BGRX8 || dst->format == OVRFSR_FORMAT_RGB32F) return OVRFSR_ERR_UNSUPPORTED; /* source-only formats */
   if (src->sample_count > 1 || dst->sample_count > 1) return OVRFSR_ERR_UNSUPPORTED; /* resolve first (ovrfsr_resolve_msaa / ovrfsr_apply) */
   if (dst->format == OVRFSR_FORMAT_BGRA8) return OVRFSR_ERR_UNSUPPORTED; /* outputs are RGBA8 / RGB10A2 (reference) or float */
   if ((dst->format == OVRFSR_FORMAT_RGB10A2) != (src->format == OVRFSR_FORMAT_RGB10A2) && dst->format != OVRFSR_FORMAT_RGBA16F &&
@@ -520,6 +588,8 @@ static int check_pair(const ovrfsr_image *src, const ovrfsr_image *dst) {
 
 int ovrfsr_dispatch_fsr_easu(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[24], int math_mode,
                              void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = untagged(src); src = &src_untagged_; }
   if (!consts) return OVRFSR_ERR_INVALID;
   int rc = check_pair(src, dst);
   if (rc != OVRFSR_OK) return rc;
@@ -532,6 +602,8 @@ int ovrfsr_dispatch_fsr_easu(const ovrfsr_image *src, const ovrfsr_image *dst, c
 
 int ovrfsr_dispatch_fsr_fused(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t upscale_consts[24],
                               const uint32_t sharpen_consts[12], int math_mode, void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = untagged(src); src = &src_untagged_; }
   if (!upscale_consts || !sharpen_consts) return OVRFSR_ERR_INVALID;
   int rc = check_pair(src, dst);
   if (rc != OVRFSR_OK) return rc;
@@ -545,6 +617,8 @@ int ovrfsr_dispatch_fsr_fused(const ovrfsr_image *src, const ovrfsr_image *dst, 
 
 int ovrfsr_dispatch_fsr_rcas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[12], int math_mode,
                              void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = untagged(src); src = &src_untagged_; }
   if (!consts) return OVRFSR_ERR_INVALID;
   int rc = check_pair(src, dst);
   if (rc != OVRFSR_OK) return rc;
@@ -593,6 +667,8 @@ void ovrfsr_cas_setup(uint32_t consts[8], float sharpness, float max_color_delta
 
 int ovrfsr_dispatch_cas(const ovrfsr_image *src, const ovrfsr_image *dst, const uint32_t consts[8], int sharpen_only, int math_mode,
                         void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = untagged(src); src = &src_untagged_; }
   if (!consts) return OVRFSR_ERR_INVALID;
   int rc = check_pair(src, dst);
   if (rc != OVRFSR_OK) return rc;

@@ -102,7 +102,7 @@ __device__ __forceinline__ float4 decode_rgb10a2(uint32_t p) {
 }
 // formats stored as one 32-bit word per texel (the TMA tile loaders handle exactly these)
 __host__ __device__ constexpr bool packed32(int fmt) {
-  return fmt == OVRFSR_FORMAT_RGBA8 || fmt == OVRFSR_FORMAT_BGRA8 || fmt == OVRFSR_FORMAT_RGB10A2;
+  return fmt == OVRFSR_FORMAT_RGBA8 || fmt == OVRFSR_FORMAT_BGRA8 || fmt == OVRFSR_FORMAT_RGB10A2 || fmt == OVRFSR_FORMAT_BGRX8;
 }
 
 // Fast-math decode of byte K: PRMT builds the float 2^23+v, one FFMA computes (2^23+v)*r - 2^23*r = fl(v*r) with a

@@ -50,6 +50,7 @@ struct RcasArgs {
   uint32_t centre[4];
   uint32_t radiusSq;
   int skipOutside;          // the preceding EASU launch already wrote the outside-radius groups to dst (EasuArgs::direct)
+  int opaqueSrc;            // B8G8R8X8 source: the X byte reads as alpha 1 (only the outside-radius copy looks at alpha)
 };
 
 // out pixel -> source position; the same instruction sequence is used for the tile origin and
@@ -349,7 +350,9 @@ __device__ __forceinline__ float4 mid_roundtrip(float r, float g, float b) {
 constexpr int kEasuRowsPerThread = 5;  // tile rows handled by one warp: ceil(37 / 8)
 constexpr int kEasuColsPerThread = 3;  // 32-wide column blocks: ceil(72 / 32)
 
-template <int FIN, int FOUT, int TW, bool TMA>
+// PAIRED = RCAS follows in the same apply (EasuArgs::direct is set): a compile-time variant, so that the plain dispatch
+// keeps exactly the instruction stream it had without the pairing.
+template <int FIN, int FOUT, int TW, bool TMA, bool PAIRED>
 __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant__ EasuArgs a,
                                                            const __grid_constant__ CUtensorMap srcMap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
         }
       } else {
         const BilinAxis ax = easu_bilinear_axis(x, a.radW, a.src.w, tx0, cols);
-        const bool direct = a.direct.ptr != nullptr;
+        constexpr bool direct = PAIRED && (FOUT == OVRFSR_FORMAT_RGBA8 || FOUT == OVRFSR_FORMAT_RGB10A2);
         // the intermediate is still needed where RCAS of an edge-adjacent inside group reads across the group edge
         const bool mid = !direct || group_inside(ggx * 16u - 8u, ggy * 16u + 8u, a.centre, a.radiusSq) ||
                          group_inside(ggx * 16u + 24u, ggy * 16u + 8u, a.centre, a.radiusSq) ||
@@ -519,8 +522,8 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
           if (y >= a.dst.h) break;
           const float3 c = easu_bilinear(sC, TW, ax, sRowAxis[y - oy0]);
           if (mid) store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
-          if constexpr (FOUT == OVRFSR_FORMAT_RGBA8 || FOUT == OVRFSR_FORMAT_RGB10A2) {
-            if (direct) {
+          if constexpr (direct) {
+            {
               uint8_t *row = a.direct.ptr + (size_t)y * a.direct.pitch;
               if (a.tintGB == 1.0f) {
                 // RCAS's copy is the identity on UNORM codes (decode -> x1 -> encode): the same bits go to the final image
@@ -634,7 +637,8 @@ __device__ __forceinline__ void store_quad(const ImageRW &dst, bool vec, int x, 
 // (profiles/r2_rejected_experiments.md).
 // skipOutside (ctx path, EASU ran with EasuArgs::direct): outside-radius groups are already final in dst, so CTAs
 // without an inside group return at once and outside groups of mixed tiles store nothing.
-template <int FIN, int FOUT, bool TMA>
+// PAIRED = skipOutside, OPQ = opaqueSrc as compile-time variants (the plain dispatch keeps its instruction stream).
+template <int FIN, int FOUT, bool TMA, bool PAIRED, bool OPQ>
 __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant__ RcasArgs a,
                                                            const __grid_constant__ CUtensorMap srcMap) {
   __shared__ __align__(128) float4 sC[kRcasTH * kRcasTW];
@@ -646,10 +650,8 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
   // same UNORM layout in and out: outside-radius texels pass through bit for bit
   constexpr bool kRawCopy = FIN == FOUT && (FIN == OVRFSR_FORMAT_RGBA8 || FIN == OVRFSR_FORMAT_RGB10A2);
 
-  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
-  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
-  if (a.skipOutside) {
-    // uniform per CTA: nothing of this tile is inside the radius -> nothing to do (also no TMA load was issued yet)
+  if constexpr (PAIRED) {
+    // uniform per CTA: nothing of this tile is inside the radius -> nothing to do (and no TMA load is issued)
     bool any = false;
 #pragma unroll
     for (int g = 0; g < 8; ++g)
@@ -664,6 +666,8 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       tma_load_2d(sRaw, &srcMap, ox0 - 4, sy0, &tileBar); // x origin 16-byte aligned: 3 unused texels on the left
     }
   }
+  const uint32_t ggx = blockIdx.x * (kTileW / 16) + (warp & 3), ggy = blockIdx.y * (kTileH / 16) + (warp >> 2);
+  const bool inside = group_inside(ggx * 16u + 8u, ggy * 16u + 8u, a.centre, a.radiusSq);
 
   if constexpr (TMA) {
     // a CTA whose 8 groups are all outside the radius and copy raw bytes needs no decoded tile at all
@@ -672,7 +676,11 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
     mbar_wait(&tileBar, 0);
     if (needTile)
       for (int ty = warp; ty < kRcasTH; ty += kThreads / 32)
-        for (int tx = lane; tx < kTileW + 2; tx += 32) sC[ty * kRcasTW + tx] = decode_rgba<FIN>(sRaw[ty * kRcasRawW + tx + 3]);
+        for (int tx = lane; tx < kTileW + 2; tx += 32) {
+          float4 c = decode_rgba<FIN>(sRaw[ty * kRcasRawW + tx + 3]);
+          if constexpr (OPQ) c.w = 1.0f;
+          sC[ty * kRcasTW + tx] = c;
+        }
   } else {
     // Texture2D.Load semantics: out of bounds reads 0 (fsr_rcas.hlsl:18)
     for (int ty = warp; ty < kRcasTH; ty += kThreads / 32) {
@@ -682,7 +690,10 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       for (int tx = lane; tx < kTileW + 2; tx += 32) {
         const int gx = sx0 + tx;
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rowOk && gx >= 0 && gx < a.src.w) c = fetch_texel<FIN>(row, gx);
+        if (rowOk && gx >= 0 && gx < a.src.w) {
+          c = fetch_texel<FIN>(row, gx);
+          if constexpr (OPQ) c.w = 1.0f;
+        }
         sC[ty * kRcasTW + tx] = c;
       }
     }
@@ -704,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 2) rcas_kernel(const __grid_constant
       store_opaque<FOUT>(a.dst.ptr + (size_t)y * a.dst.pitch, x, c.x, c.y, c.z);
       b = e; e = h; p += kRcasTW;
     }
-  } else if (!a.skipOutside) {
+  } else if constexpr (!PAIRED) {
     // OutputTexture[p] = mul * InputTexture[p], alpha included (fsr_rcas.hlsl:45-53)
     if constexpr (TMA && kRawCopy) {
       if (a.tintGB == 1.0f) {

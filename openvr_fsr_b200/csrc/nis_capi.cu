@@ -41,8 +41,8 @@ namespace {
 inline uint32_t bpp(int fmt) { return fmt == OVRFSR_FORMAT_RGBA32F ? 16u : (fmt == OVRFSR_FORMAT_RGBA16F ? 8u : 4u); }
 int check(const ovrfsr_image *im, bool isDst) {
   if (!im || !im->data || im->width == 0 || im->height == 0) return OVRFSR_ERR_INVALID;
-  if (im->format < OVRFSR_FORMAT_RGBA8 || im->format > OVRFSR_FORMAT_RGB10A2) return OVRFSR_ERR_UNSUPPORTED;
-  if ((isDst && im->format == OVRFSR_FORMAT_BGRA8) || im->sample_count > 1) return OVRFSR_ERR_UNSUPPORTED;
+  if (im->format < OVRFSR_FORMAT_RGBA8 || im->format > OVRFSR_FORMAT_BGRX8) return OVRFSR_ERR_UNSUPPORTED; /* RGB32F: expand first */
+  if ((isDst && (im->format == OVRFSR_FORMAT_BGRA8 || im->format == OVRFSR_FORMAT_BGRX8)) || im->sample_count > 1) return OVRFSR_ERR_UNSUPPORTED;
   if (im->pitch < im->width * bpp(im->format) || im->pitch % bpp(im->format) ||
       reinterpret_cast<uintptr_t>(im->data) % bpp(im->format)) return OVRFSR_ERR_INVALID;
   return OVRFSR_OK;
@@ -58,6 +58,8 @@ extern "C" {
 
 int ovrfsr_dispatch_nis_scaler(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256, int math_mode,
                                void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = *src; if (src_untagged_.format >= 0) src_untagged_.format &= OVRFSR_FORMAT_LAYOUT_MASK; src = &src_untagged_; }
   if (!cfg256) return OVRFSR_ERR_INVALID;
   int rc = check(src, false);
   if (rc != OVRFSR_OK || (rc = check(dst, true)) != OVRFSR_OK) return rc;
@@ -72,6 +74,8 @@ int ovrfsr_dispatch_nis_scaler(const ovrfsr_image *src, const ovrfsr_image *dst,
 
 int ovrfsr_dispatch_nis_sharpen(const ovrfsr_image *src, const ovrfsr_image *dst, const void *cfg256, int math_mode,
                                 void *stream) {
+  ovrfsr_image src_untagged_{};
+  if (src) { src_untagged_ = *src; if (src_untagged_.format >= 0) src_untagged_.format &= OVRFSR_FORMAT_LAYOUT_MASK; src = &src_untagged_; }
   if (!cfg256) return OVRFSR_ERR_INVALID;
   int rc = check(src, false);
   if (rc != OVRFSR_OK || (rc = check(dst, true)) != OVRFSR_OK) return rc;

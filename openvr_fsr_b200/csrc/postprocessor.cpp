@@ -62,7 +62,10 @@ void PostProcessor::Apply(EVREye eEye, const Texture_t *pTexture, const VRTextur
       enabled = false;
       return;
     }
-    inputIsSrgb = pTexture->eColorSpace == ColorSpace_Gamma;
+    // PostProcessor.cpp:504: Gamma, or Auto on a format OpenVR treats as sRGB (the _SRGB / _TYPELESS DXGI variants,
+    // carried as tag bits of ovrfsr_image::format)
+    inputIsSrgb = pTexture->eColorSpace == ColorSpace_Gamma ||
+                  (pTexture->eColorSpace == ColorSpace_Auto && ovrfsr_format_considered_srgb(texture->format));
     Log() << "Creating post-processing resources\n";
     Log() << "Using " << (k.use_nis ? "NVIDIA Image Scaling" : "AMD FidelityFX SuperResolution") << "\n";
     initialized = true;

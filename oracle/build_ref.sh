@@ -13,6 +13,7 @@
 #   nis_ref_{scaler,sharpen}.cpp : NIS_Scaler.h verbatim (NIS_SCALER=1 / 0) behind an HLSL type shim
 #   cas_consts_ref.cpp : src/cas/ffx_a.h + ffx_cas.h under A_CPU, as shipped (CasSetup)
 #   cas_ref.cpp    : src/cas/ffx_cas.h:409-893 (CasFilter), src/cas/ffx_a.h:1455-1457, behind the same type shim
+#   dds_ref.cpp    : src/postprocess/ScreenGrab11.cpp:72-208 (DDS structs / pixel-format table) and :819-887 (header fill)
 # The reference's own build system (Visual Studio + fxc, src/CMakeLists.txt:155-170) is not run.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -53,8 +54,17 @@ sed -n '1455p' "$CASA" | grep -q 'APrxLoSqrtF1'        || { echo "CAS anchor 145
 sed -n '409,893p' "$CAS" | sed -E "$HLSL2CPP" > "$TMP/cas_lines.inc"
 sed -n '1455,1457p' "$CASA" > "$TMP/cas_prx.inc"
 
+# the capture path's DDS container: the reference's own header structs, pixel-format table and fill
+GRAB="$REF/src/postprocess/ScreenGrab11.cpp"
+sed -n '72p' "$GRAB" | grep -q 'pragma pack(push,1)'          || { echo "DDS anchor 72 moved"; exit 1; }
+sed -n '208p' "$GRAB" | grep -q "MAKEFOURCC('D','X','1','0')"  || { echo "DDS anchor 208 moved"; exit 1; }
+sed -n '819p' "$GRAB" | grep -q 'MAX_HEADER_SIZE'              || { echo "DDS anchor 819 moved"; exit 1; }
+sed -n '887p' "$GRAB" | grep -q '^    }$'                      || { echo "DDS anchor 887 moved"; exit 1; }
+sed -n '72,208p' "$GRAB" > "$TMP/dds_structs.inc"
+sed -n '819,887p' "$GRAB" > "$TMP/dds_setup.inc"
+
 OBJS=()
-for f in consts_ref fsr_ref nis_ref_scaler nis_ref_sharpen cas_consts_ref cas_ref; do
+for f in consts_ref fsr_ref nis_ref_scaler nis_ref_sharpen cas_consts_ref cas_ref dds_ref; do
   [ -f "$HERE/ref_shim/$f.cpp" ] || continue
   $CXX $CXXFLAGS -I"$REF/src" -I"$TMP" -c "$HERE/ref_shim/$f.cpp" -o "$TMP/$f.o"
   OBJS+=("$TMP/$f.o")

@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-FMT_RGBA8, FMT_BGRA8, FMT_RGBA16F, FMT_RGBA32F, FMT_RGB10A2 = 0, 1, 2, 3, 4
+FMT_RGBA8, FMT_BGRA8, FMT_RGBA16F, FMT_RGBA32F, FMT_RGB10A2, FMT_BGRX8, FMT_RGB32F = 0, 1, 2, 3, 4, 5, 6
 
 
 class Image(C.Structure):
@@ -123,6 +123,19 @@ def oracle_lib():
     return _oracle
 
 
+DXGI_OF_FORMAT = {FMT_RGBA8: 28, FMT_BGRA8: 87, FMT_RGBA16F: 10, FMT_RGBA32F: 2, FMT_RGB10A2: 24}  # dxgiformat.h values
+
+
+def ref_dds_header(width: int, height: int, fmt: int, bytes_per_texel: int) -> bytes:
+    """The DDS file header SaveDDSTextureToFile writes (ScreenGrab11.cpp:72-208,819-906 compiled from the reference's own
+    lines, oracle/ref_shim/dds_ref.cpp) for an uncompressed texture of ovrfsr format `fmt` with tight rows."""
+    buf = (C.c_uint8 * 148)()
+    n = ref_lib().ref_dds_header(buf, width, height, DXGI_OF_FORMAT[fmt], width * bytes_per_texel)
+    if n <= 0:
+        raise RuntimeError(f"reference rejects the format (rc={n})")
+    return bytes(buf[:n])
+
+
 def ref_available() -> bool:
     build()
     return (HERE / "_ref" / "libovrfsr_ref.so").exists()
@@ -161,6 +174,9 @@ def _np_format(arr: np.ndarray, fmt: int | None) -> int:
 
 def as_image(arr: np.ndarray, fmt: int | None = None) -> Image:
     """arr: (H, W, 4) uint8, float16 or float32, C-contiguous rows (row pitch = arr.strides[0])."""
+    if fmt == FMT_RGB32F:  # R32G32B32_FLOAT source: (H, W, 3) float32
+        assert arr.ndim == 3 and arr.shape[2] == 3 and arr.dtype == np.float32 and arr.strides[1] == 12
+        return Image(arr.ctypes.data, arr.shape[1], arr.shape[0], arr.strides[0], fmt)
     assert arr.ndim == 3 and arr.shape[2] == 4 and arr.dtype in (np.uint8, np.float16, np.float32)
     assert arr.strides[2] == arr.itemsize and arr.strides[1] == 4 * arr.itemsize
     return Image(arr.ctypes.data, arr.shape[1], arr.shape[0], arr.strides[0], _np_format(arr, fmt))

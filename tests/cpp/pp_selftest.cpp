@@ -88,6 +88,24 @@ int main(int argc, char **argv) {
     const ovrfsr_image *out = static_cast<const ovrfsr_image *>(t.handle);
     std::printf("capture requested: %ux%u\n", out->width, out->height);
   }
+  // 5. the colour-space tag handed on to the real Submit (PostProcessor.cpp:162,504): Gamma stays Gamma; Auto becomes
+  // Gamma exactly for the formats IsConsideredSrgbByOpenVR names (:76-92), carried as tag bits of the image format
+  struct { int32_t fmt; vr::EColorSpace in, want; } cases[] = {
+      {OVRFSR_FORMAT_RGBA8, vr::ColorSpace_Auto, vr::ColorSpace_Auto},
+      {OVRFSR_FORMAT_RGBA8 | OVRFSR_FORMAT_SRGB_BIT, vr::ColorSpace_Auto, vr::ColorSpace_Gamma},
+      {OVRFSR_FORMAT_RGBA8 | OVRFSR_FORMAT_TYPELESS_BIT, vr::ColorSpace_Auto, vr::ColorSpace_Gamma},
+      {OVRFSR_FORMAT_RGBA8 | OVRFSR_FORMAT_SRGB_BIT, vr::ColorSpace_Linear, vr::ColorSpace_Auto},
+      {OVRFSR_FORMAT_RGBA8, vr::ColorSpace_Gamma, vr::ColorSpace_Gamma},
+  };
+  for (const auto &c : cases) {
+    postProcessor.Reset(); // inputIsSrgb is decided when the resources are (re)created, like the reference
+    ovrfsr_image tagged = eye[0];
+    tagged.format = c.fmt;
+    vr::Texture_t t{&tagged, vr::TextureType_OvrFsrCuda, c.in};
+    postProcessor.Apply(vr::Eye_Left, &t, &bounds, vr::Submit_Default);
+    if (t.handle == &tagged) return fail("tagged format was not processed");
+    if (t.eColorSpace != c.want) return fail("colour-space tag differs from PostProcessor.cpp:162,504");
+  }
   for (int e = 0; e < 2; ++e) ovrfsr_image_free(&eye[e]);
   return 0;
 }

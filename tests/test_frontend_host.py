@@ -101,3 +101,37 @@ def test_resolve_restatement_properties():
     assert fe.resolve_msaa(two, 2, fe.FMT_RGBA8).tolist() == [[[128, 128, 128, 128]]]
     ten = synth.uniform_rgb10a2(10, 5, 2)
     assert np.array_equal(fe.resolve_msaa(np.repeat(ten, 4, axis=1), 4, fe.FMT_RGB10A2), ten)
+
+
+def _dds_header_of_library(tmp_path, fmt, w, h, bpt):
+    """Header bytes of the file the product's writer (capture.cpp, ovrfsr_dds_write) produces for a w x h image."""
+    import ctypes as C
+    from openvr_fsr_b200 import _lib as L
+    buf = np.zeros((h, w * bpt), dtype=np.uint8)
+    im = L.Image(buf.ctypes.data, w, h, w * bpt, fmt, 1, 0, 0)
+    p = tmp_path / f"h_{fmt}_{w}x{h}.dds"
+    assert L.lib().ovrfsr_dds_write(str(p).encode(), C.byref(im)) == L.OK
+    data = p.read_bytes()
+    return data[: len(data) - buf.nbytes]
+
+
+def test_dds_header_equals_the_reference_writers(tmp_path):
+    """Pins the capture container to the reference: tests/golden/dds_headers.json holds the headers produced by
+    SaveDDSTextureToFile's own lines (ScreenGrab11.cpp:72-208,819-906 compiled into oracle/_ref, see
+    tests/golden/make_golden_dds.py); the library's writer and the numpy restatement must reproduce them byte for byte."""
+    import json
+    from pathlib import Path
+    from oracle import pyoracle as po
+    cases = json.loads((Path(__file__).parent / "golden" / "dds_headers.json").read_text())
+    assert len(cases) == 15
+    for c in cases:
+        want = bytes.fromhex(c["header_hex"])
+        if c["width"] * c["height"] <= 1 << 20:  # the 2244x2492 header only from the cheap paths below
+            got = _dds_header_of_library(tmp_path, c["format"], c["width"], c["height"], c["bytes_per_texel"])
+            assert got == want, c
+        dt = {fe.FMT_RGBA16F: np.float16, fe.FMT_RGBA32F: np.float32}.get(c["format"], np.uint8)
+        if c["width"] * c["height"] <= 1 << 20:
+            blob = fe.dds_bytes(np.zeros((c["height"], c["width"], 4), dt), c["format"])
+            assert blob[: len(want)] == want, c
+        if po.ref_available():  # the fixture itself against a fresh run of the reference lines
+            assert po.ref_dds_header(c["width"], c["height"], c["format"], c["bytes_per_texel"]) == want

@@ -114,3 +114,27 @@ def test_f7_capture_writes_the_left_eye_output(cuda, tmp_path):
     with open(pp.last_capture_path(), "rb") as f:
         assert f.read() == fe.dds_bytes(out10, fe.FMT_RGB10A2)
     pp.close()
+
+
+@pytest.mark.parametrize("samples", [2, 4, 8])
+def test_resolve_is_the_exact_sample_mean_within_unorm_rounding(cuda, samples):
+    """An independent statement of ResolveSubresource for UNORM targets (D3D11 functional spec: the resolved value is
+    the average of the samples, written with the FLOAT -> UNORM conversion whose tolerance is 0.6 ULP): computed here in
+    exact integer arithmetic, not through oracle/frontend.py.  |code - exact mean| <= 0.5 (+ float slack) everywhere,
+    and equal to round-half-up of the exact mean wherever the mean is not within 1e-3 of a .5 tie."""
+    import torch
+    import openvr_fsr_b200 as ovr
+    w, h = 67, 41
+    rng = np.random.default_rng(samples)
+    src = rng.integers(0, 256, (h, w * samples, 4), dtype=np.uint8)
+    src[:, : 8 * samples] = np.repeat(rng.integers(0, 256, (h, 8, 4), dtype=np.uint8), samples, axis=1)  # some flat texels
+    dst = torch.zeros((h, w, 4), dtype=torch.uint8, device=cuda)
+    ovr.resolve_msaa(torch.from_numpy(src).to(cuda), dst, samples)
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy().astype(np.float64)
+    exact = src.reshape(h, w, samples, 4).astype(np.int64).sum(axis=2) / samples
+    assert np.abs(got - exact).max() <= 0.5 + 1e-3
+    frac = exact - np.floor(exact)
+    clear = np.abs(frac - 0.5) > 1e-3
+    assert np.array_equal(got[clear], np.floor(exact + 0.5)[clear])
+    assert np.array_equal(got[:, :8], src[:, : 8 * samples : samples].astype(np.float64))  # identical samples resolve to themselves

@@ -107,7 +107,10 @@ def test_full_frame_c2_strict_bit_exact_and_fast_statistics(cuda):
         pp.close()
         print(f"radius {radius}: fast per-pass mismatch EASU {(de > 0).mean():.2e} RCAS {(dr > 0).mean():.2e}; "
               f"composed: {(comp > 1).mean():.2e} of channel values beyond 1 LSB, max {comp.max()}")
-        assert (comp > 1).mean() < 1e-3
+        # measured over the C2-sized natural / noise images (tools/fastmath_error.py, profiles/r2_fastmath_composed_error.txt):
+        # max 3 LSB, 6e-6 of the channel values beyond 1 LSB -- a 1-LSB difference in the RGBA8 intermediate is
+        # amplified where RCAS divides by a dark ring maximum
+        assert comp.max() <= 4 and (comp > 1).mean() < 1e-4
 
 
 @pytest.mark.parametrize("iw,ih,scale", [(33, 47, 0.75), (211, 157, 0.75), (129, 65, 0.59), (100, 40, 1.0 / 1.07), (77, 50, 0.5)])

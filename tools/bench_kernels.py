@@ -40,3 +40,19 @@ for math, mname in ((ovr.MATH_STRICT, "strict"), (ovr.MATH_FAST, "fast")):
         tn = timeit(lambda i: ovr.nis_scaler(npool[i], ndst, scfg, math))
         out.append(f"{mname} r{radius}: NVScaler {tn:6.1f}")
 print(os.environ.get("OVRFSR_LIB", "current"), " | ".join(out))
+# C3b: RCAS only on a 2915x3240 RGBA16F frame -> RGBA8 (plain-load tile path), radius 0.5
+cw, ch = 2915, 3240
+f16 = [torch.from_numpy(np.roll(synth.natural_rgba16f(cw, ch, 3), 37 * i, axis=0)).to(dev) for i in range(4)]
+cdst = ovr.alloc_image(cw, ch, torch.uint8, dev)
+o2 = []
+for math, mname in ((ovr.MATH_STRICT, "strict"), (ovr.MATH_FAST, "fast")):
+    cfg = ovr.Config(fsrEnabled=True, renderScale=1.0, sharpness=0.9, radius=0.5, mathMode=math)
+    sc = ovr.make_sharpen_constants(cfg, 0, True, cw, ch)
+    marks = []
+    for rep in range(8):
+        for i in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ovr.fsr_rcas(f16[i], cdst, sc, math); e1.record(); marks.append((e0, e1))
+    torch.cuda.synchronize()
+    o2.append(f"{mname} C3b RCAS fp16 {statistics.mean(a.elapsed_time(b) for a, b in marks[4:]) * 1e3:6.1f}")
+print(" | ".join(o2))
