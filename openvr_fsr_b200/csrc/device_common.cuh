@@ -209,7 +209,7 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 // are therefore FMAs against NEUTRAL ELEMENTS THE COMPILER CANNOT SEE: a __constant__ pair (-0, 1) that the host could
 // overwrite, so it is loaded at run time.  fma(a, b, -0) = rn(a*b) and fma(a, 1, b) = rn(a+b) exactly (including
 // the sign of zero), each a single rounding, and two real FMAs cannot be merged.
-__constant__ float g_neutral[2] = {-0.0f, 1.0f};
+__constant__ float g_neutral[3] = {-0.0f, 1.0f, -1.0f};
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   if constexpr (kStrict) return __ffma2_rn(a, b, bc(g_neutral[0]));
   else return __fmul2_rn(a, b);
@@ -217,6 +217,21 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
 __device__ __forceinline__ f2 add2(f2 a, f2 b) {
   if constexpr (kStrict) return __ffma2_rn(a, bc(g_neutral[1]), b);
   else return __fadd2_rn(a, b);
+}
+
+// a - b, a*sa + b*sb and the HLSL lerp x + s*(y - x) on two lanes: in strict math every product and sum is its own
+// rounding (explicit FMAs against the opaque neutral elements, see above); fast math contracts like the scalar code does
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  if constexpr (kStrict) return __ffma2_rn(b, bc(g_neutral[2]), a); // b * -1 is exact
+  else return __ffma2_rn(b, bc(-1.0f), a);
+}
+__device__ __forceinline__ f2 madd2(f2 a, f2 sa, f2 b, f2 sb) {
+  if constexpr (kStrict) return add2(mul2(a, sa), mul2(b, sb));
+  else return fma2(b, sb, mul2(a, sa));
+}
+__device__ __forceinline__ f2 lerp2(f2 x, f2 y, f2 s) {
+  if constexpr (kStrict) return add2(x, mul2(s, sub2(y, x)));
+  else return fma2(s, sub2(y, x), x);
 }
 
 // Coordinate arithmetic is NEVER contracted, in either math mode: its result feeds floor()/int conversion, and a
