@@ -20,7 +20,7 @@ for l in res.split("\n"):
         regs[cur] = (int(m.group(1)), int(m.group(2)))
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n
 COLS = OrderedDict([
-    ("UTMALDG", r"^UTMALDG"), ("UTMASTG", r"^UTMASTG"), ("UBLKCP", r"^UBLKCP"), ("SYNCS", r"^SYNCS"),
+    ("UTMALDG", r"^UTMALDG"), ("UTMASTG", r"^UTMASTG"), ("UBLKCP", r"^UBLKCP"), ("SYNCS", r"^SYNCS"), ("UGETNEXTWORKID", r"^UGETNEXTWORKID"),
     ("FFMA2", r"^FFMA2"), ("FMUL2", r"^FMUL2"), ("FADD2", r"^FADD2"), ("FFMA", r"^FFMA\b"), ("FMUL", r"^FMUL\b"), ("FADD", r"^FADD\b"),
     ("STG.32", r"^STG\.E\s"), ("STG.64", r"^STG\.E\.64"), ("STG.128", r"^STG\.E\.128"),
     ("LDG.128", r"^LDG\.E\.128"), ("LDS.32", r"^LDS\s"), ("LDS.64", r"^LDS\.64"), ("LDS.128", r"^LDS\.128"), ("STS.128", r"^STS\.128"),
@@ -42,7 +42,7 @@ for b in blocks[1:]:
                 c[k] += 1
     rows.append((name, len(ins), c))
 print(f"# static SASS instruction counts per kernel of {Path(lib).name} (cuobjdump -sass; sm_100a only)")
-print("# TMA loads = UTMALDG, TMA stores = UTMASTG, mbarrier = SYNCS, packed FP32x2 = FFMA2 / FMUL2 / FADD2")
+print("# TMA loads = UTMALDG, TMA stores = UTMASTG, mbarrier = SYNCS, cluster launch control = UGETNEXTWORKID, packed FP32x2 = FFMA2 / FMUL2 / FADD2")
 tot = Counter()
 for name, n, c in sorted(rows, key=lambda r: r[0]):
     d = demangle(name)
