@@ -26,6 +26,10 @@ for math in (ovr.MATH_STRICT, ovr.MATH_FAST):
                 ten = fmt == ovr.FORMAT_RGB10A2
                 mid = ovr.alloc_image(ow, oh, torch.uint8, dev)
                 out = ovr.alloc_image(ow, oh, torch.uint8, dev)
+                if scale != 1.0 and src.dtype == torch.uint8:  # round 2: the fused EASU->RCAS kernel on the same inputs
+                    fz = ovr.alloc_image(ow, oh, torch.uint8, dev)
+                    ovr.fsr_fused(src, fz, uc, sc, math, src_fmt=fmt, dst_fmt=ovr.FORMAT_RGB10A2 if ten else None)
+                    n += 1
                 if scale != 1.0:
                     ovr.fsr_easu(src, mid, uc, math, src_fmt=fmt, dst_fmt=ovr.FORMAT_RGB10A2 if ten else None)
                     ovr.fsr_rcas(mid, out, sc, math, src_fmt=ovr.FORMAT_RGB10A2 if ten else None,
@@ -57,6 +61,22 @@ for math in (ovr.MATH_STRICT, ovr.MATH_FAST):
                 out = ovr.alloc_image(ow, oh, torch.uint8, dev)
                 (ovr.nis_sharpen if scale == 1.0 else ovr.nis_scaler)(src, out, ncfg, math)
                 n += 1
+    torch.cuda.synchronize()
+# round 2: paired passes through the context (masked and unmasked), BGRX8 / RGB32F sources, NVScaler over many blocks
+for math in (ovr.MATH_STRICT, ovr.MATH_FAST):
+    for radius in (2.0, 0.35):
+        pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=0.75, sharpness=0.9, radius=radius, mathMode=math))
+        pp.apply(0, ovr.to_image(synth.natural_rgba8(331, 203, 11), dev))
+        pp.apply(1, ovr.to_image(synth.natural_rgba8(331, 203, 12), dev), fmt=ovr.FORMAT_BGRX8 | ovr.FORMAT_SRGB_BIT)
+        pp.close()
+        pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=0.75, sharpness=0.9, radius=radius, mathMode=math, fusedFsr=True))
+        pp.apply(0, ovr.to_image(synth.natural_rgba8(331, 203, 13), dev))
+        pp.close()
+        pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, useNis=True, renderScale=0.75, sharpness=0.9, radius=radius, mathMode=math))
+        pp.apply(0, ovr.to_image(synth.natural_rgba8(331, 203, 14), dev))
+        pp.apply(1, torch.from_numpy(synth.natural_rgba8(331, 203, 15)).to(dev), fmt=ovr.FORMAT_BGRX8)
+        pp.apply(0, torch.from_numpy(np.ascontiguousarray(synth.natural_rgba16f(120, 90, 2).astype(np.float32)[..., :3])).to(dev), fmt=ovr.FORMAT_RGB32F)
+        pp.close()
     torch.cuda.synchronize()
 # front end + stateful path + host entry
 ms = torch.from_numpy(np.repeat(synth.natural_rgba8(90, 61, 7), 4, axis=1)).to(dev)
