@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objdir.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + \
         [PKG.parent / "include" / "ovrfsr.h", Path(__file__)]
-    objs = []
+    objs, jobs = [], []
     for name, extra in UNITS.items():
         src = CSRC / name
         if not src.exists():
@@ -58,8 +58,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))
-            subprocess.check_call(cmd)
+            jobs.append(cmd)
         objs.append(obj)
+    # the two kernel translation units dominate (~50 s each): compile the stale units side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(4, os.cpu_count() or 1)) as pool:
+        for rc in pool.map(lambda c: subprocess.call(c), jobs):
+            if rc != 0:
+                raise subprocess.CalledProcessError(rc, "nvcc")
     if force or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", str(LIB), *map(str, objs), "-lpthread", "-ldl"]
         subprocess.check_call(cmd)
