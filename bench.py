@@ -393,6 +393,9 @@ def main():
         extras["value_one_stream"] = {"value": world * quick_value(ovr, torch, cfg, pool, n, 1),
                                       "masked_r0.5": world * quick_value(ovr, torch, dataclasses.replace(cfg, radius=0.5), pool, n, 1),
                                       "unit": "pairs/s", "note": "everything strictly back to back on ONE stream (a VR render thread)"}
+        extras["value_one_stream_pair"] = {"value": world * quick_value(ovr, torch, cfg, pool, n, 1, pair=True),
+                                           "masked_r0.5": world * quick_value(ovr, torch, dataclasses.replace(cfg, radius=0.5), pool, n, 1, pair=True),
+                                           "unit": "pairs/s", "note": "ONE caller stream, both eyes per call (ovrfsr_apply_pair: the right eye forked onto a ctx-owned stream and joined back)"}
         extras["c5_strong"] = c5_strong(ovr, torch, dist, cfg, pool, dev, rank, world, args.streams)
         if world == 2:
             extras["c4_eye_sharded"] = c4_eye_sharded(ovr, torch, dist, synth, sharding, dev, rank, math_mode)
@@ -487,7 +490,8 @@ class EyeStreams:
     context i % n_ctx.  Kernels of different eyes / frames then share the SMs: a persistent grid's last wave no
     longer leaves SMs idle."""
 
-    def __init__(self, ovr, torch, cfg, dev, n_streams):
+    def __init__(self, ovr, torch, cfg, dev, n_streams, pair=False):
+        self.pair = pair  # one caller stream, both eyes handed over in one PostProcessor.apply_pair call
         self.main = torch.cuda.current_stream(dev)
         self.pps = [ovr.PostProcessor(cfg) for _ in range(max(1, n_streams // 2))]
         if n_streams == 1:
@@ -499,6 +503,9 @@ class EyeStreams:
         n = len(self.pps)
         for i in (range(len(pool)) if frames is None else frames):
             left, right = pool[i % len(pool)]
+            if self.pair:
+                self.pps[i % n].apply_pair(left, right, stream=self.streams[i % n][0])
+                continue
             self.pps[i % n].apply(0, left, stream=self.streams[i % n][0])
             self.pps[i % n].apply(1, right, stream=self.streams[i % n][1])
 
@@ -519,10 +526,10 @@ class EyeStreams:
             p.close()
 
 
-def quick_value(ovr, torch, cfg, pool, passes, n_streams):
+def quick_value(ovr, torch, cfg, pool, passes, n_streams, pair=False):
     """pairs/s of `passes` passes over the pool with the given configuration (one rank)."""
     dev = pool[0][0].device
-    r = EyeStreams(ovr, torch, cfg, dev, n_streams)
+    r = EyeStreams(ovr, torch, cfg, dev, n_streams, pair)
     for _ in range(2):
         r.pass_over(pool)
     torch.cuda.synchronize()

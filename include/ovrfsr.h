@@ -159,6 +159,17 @@ OVRFSR_API int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src, i
 OVRFSR_API int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_host, int only_one_eye,
                                  const ovrfsr_image *dst_host, void *stream);
 
+/* Both eyes of one frame in one call, for hosts that hold both textures when they submit (the reference's hook sees them
+ * one Submit at a time, VrHooks.cpp:50-66; its D3D11 context is free to overlap the two eyes' dispatches, which have no
+ * hazard between them -- a single CUDA stream is not).  Same result and same per-eye state as
+ *   ovrfsr_apply(ctx, 0, src_left, only_one_eye, &out[0], stream); ovrfsr_apply(ctx, 1, src_right, only_one_eye, &out[1], stream);
+ * but the right eye's passes run on a ctx-owned stream forked from `stream` before the left eye is queued and joined
+ * back into it before the call returns, so the tail of one eye's launches overlaps the other eye's (C2, one caller
+ * stream: see DESIGN.md section 7).  Everything queued on `stream` afterwards sees both outputs; capturable into a CUDA
+ * graph.  With only_one_eye == 0 (one texture holding both eyes) it is exactly the two calls above. */
+OVRFSR_API int ovrfsr_apply_pair(ovrfsr_ctx *ctx, const ovrfsr_image *src_left, const ovrfsr_image *src_right,
+                                 int only_one_eye, ovrfsr_image out[2], void *stream);
+
 /* ---- individual dispatches (ApplyUpscaling / ApplySharpening, PostProcessor.cpp:385-401,483-496) --
  * Stateless: explicit constant blocks, caller-owned destination.  math_mode as ovrfsr_math. */
 /* g_FSRUpscaleShader: consts = UpscaleConstants, 24 x u32 (PostProcessor.cpp:276-283) */

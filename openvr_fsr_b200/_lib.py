@@ -43,6 +43,7 @@ SYMBOLS = {
     "ovrfsr_get_config": (C.c_int, [_vp, _cfgp]),
     "ovrfsr_apply": (C.c_int, [_vp, C.c_int, _imgp, C.c_int, _imgp, _vp]),
     "ovrfsr_apply_host": (C.c_int, [_vp, C.c_int, _imgp, C.c_int, _imgp, _vp]),
+    "ovrfsr_apply_pair": (C.c_int, [_vp, _imgp, _imgp, C.c_int, _imgp, _vp]),
     "ovrfsr_dispatch_fsr_easu": (C.c_int, [_imgp, _imgp, _u32p, C.c_int, _vp]),
     "ovrfsr_dispatch_fsr_rcas": (C.c_int, [_imgp, _imgp, _u32p, C.c_int, _vp]),
     "ovrfsr_dispatch_fsr_fused": (C.c_int, [_imgp, _imgp, _u32p, _u32p, C.c_int, _vp]),

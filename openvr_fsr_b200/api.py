@@ -162,6 +162,20 @@ class PostProcessor:
         self.last_output_format = out.format  # RGBA8, or RGB10A2 for a 10-bit source (bytes of the packed u32 texels)
         return _wrap_device(out, texture.device)
 
+    def apply_pair(self, left, right, bounds: TextureBounds | None = None, fmt: int | None = None, stream=None):
+        """Both eyes of a frame in one call (ovrfsr_apply_pair): the same outputs as apply(0, left) then apply(1, right)
+        on `stream`, with the right eye's passes forked onto a ctx-owned stream and joined back before returning.
+        Returns (left_out, right_out), or the inputs on pass-through."""
+        bounds = bounds or TextureBounds()
+        only_one_eye = int(abs(bounds.uMax - bounds.uMin) > 0.5)
+        sl, sr, outs = image_of(left, fmt), image_of(right, fmt), (L.Image * 2)()
+        rc = L.lib().ovrfsr_apply_pair(self._ctx, C.byref(sl), C.byref(sr), only_one_eye, outs, _stream_ptr(stream))
+        if rc == L.PASSTHROUGH:
+            return left, right
+        L.check(rc, "ovrfsr_apply_pair", self._ctx)
+        self.last_output_format = outs[0].format
+        return _wrap_device(outs[0], left.device), _wrap_device(outs[1], right.device)
+
     def apply_host(self, eye: int, src_host, dst_host, bounds: TextureBounds | None = None, fmt: int | None = None,
                    stream=None, dst_fmt: int | None = None):
         """End-to-end entry: host (pinned) tensors in and out, copies included, asynchronous on `stream`."""

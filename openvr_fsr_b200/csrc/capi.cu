@@ -146,6 +146,9 @@ struct ovrfsr_ctx {
   int currentQuery = 0;
   float summedGpuTime = 0.f;
   int countedQueries = 0;
+  // ovrfsr_apply_pair: the right eye's chain runs on this stream between a fork and a join event
+  cudaStream_t pairStream = nullptr;
+  cudaEvent_t pairFork = nullptr, pairJoin = nullptr;
   std::string lastError;
 };
 
@@ -407,6 +410,12 @@ int ovrfsr_create(ovrfsr_ctx **out, const ovrfsr_config *cfg) {
 }
 
 void ovrfsr_destroy(ovrfsr_ctx *ctx) {
+  if (ctx && ctx->pairStream) {
+    cudaStreamSynchronize(ctx->pairStream);
+    cudaEventDestroy(ctx->pairFork);
+    cudaEventDestroy(ctx->pairJoin);
+    cudaStreamDestroy(ctx->pairStream);
+  }
   if (!ctx) return;
   if (ctx->initialized || ctx->hostStage[0].img.data || ctx->hostStage[1].img.data) {
     if (ctx->cfg.device >= 0) cudaSetDevice(ctx->cfg.device);
@@ -478,6 +487,39 @@ int ovrfsr_apply(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_tagged, int o
   ctx->eyeCount = (ctx->eyeCount + 1) % 2;
   *out = ctx->lastOutput;
   return OVRFSR_OK;
+}
+
+int ovrfsr_apply_pair(ovrfsr_ctx *ctx, const ovrfsr_image *src_left, const ovrfsr_image *src_right, int only_one_eye,
+                      ovrfsr_image out[2], void *stream) {
+  if (!ctx || !src_left || !src_right || !out) return OVRFSR_ERR_INVALID;
+  if (!ctx->enabled || !ctx->cfg.fsr_enabled) return OVRFSR_PASSTHROUGH;
+  int rc = select_device(ctx);
+  if (rc != OVRFSR_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // one texture holding both eyes is processed once (PostProcessor.cpp:155-160): nothing to run side by side
+  if (!only_one_eye) {
+    if ((rc = ovrfsr_apply(ctx, 0, src_left, 0, &out[0], stream)) != OVRFSR_OK) return rc;
+    return ovrfsr_apply(ctx, 1, src_right, 0, &out[1], stream);
+  }
+  if (!ctx->pairStream) {
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->pairStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->pairFork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->pairJoin, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail(ctx, OVRFSR_ERR_CUDA, "creating the pair stream", e);
+  }
+  // fork BEFORE the left eye is queued (the right eye must not wait for it), but queue the left eye first: it is the
+  // call that (re)creates the resources when the source size changed
+  cudaError_t e = cudaEventRecord(ctx->pairFork, s);
+  if (e != cudaSuccess) return fail(ctx, OVRFSR_ERR_CUDA, "forking the pair stream", e);
+  rc = ovrfsr_apply(ctx, 0, src_left, 1, &out[0], stream);
+  if (rc != OVRFSR_OK) return rc;
+  e = cudaStreamWaitEvent(ctx->pairStream, ctx->pairFork, 0);
+  if (e != cudaSuccess) return fail(ctx, OVRFSR_ERR_CUDA, "forking the pair stream", e);
+  rc = ovrfsr_apply(ctx, 1, src_right, 1, &out[1], ctx->pairStream);
+  e = cudaEventRecord(ctx->pairJoin, ctx->pairStream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ctx->pairJoin, 0);
+  if (e != cudaSuccess) return fail(ctx, OVRFSR_ERR_CUDA, "joining the pair stream", e);
+  return rc;
 }
 
 int ovrfsr_apply_host(ovrfsr_ctx *ctx, int eye, const ovrfsr_image *src_tagged, int only_one_eye,
