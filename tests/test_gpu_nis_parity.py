@@ -11,7 +11,13 @@ CASES = [(33, 47, 0.75), (64, 48, 0.5), (100, 77, 0.77), (151, 93, 0.6), (40, 30
 
 def _imgs(w, h):
     from openvr_fsr_b200 import synth
-    return {"uniform": synth.uniform_rgba8(w, h, 0), "natural": synth.natural_rgba8(w, h, 1)}
+    # black / grey: every pixel takes the edge-free shortcut (black also makes pixel_n * 255 a zero: the signed-zero case);
+    # textured: warps with edge-free and edge pixels side by side
+    black = np.zeros((h, w, 4), np.uint8)
+    grey = np.full((h, w, 4), 77, np.uint8)
+    black[..., 3] = grey[..., 3] = 255
+    return {"uniform": synth.uniform_rgba8(w, h, 0), "natural": synth.natural_rgba8(w, h, 1),
+            "textured": synth.textured_rgba8(w, h, 3, cell=16), "black": black, "grey": grey}
 
 
 @pytest.mark.parametrize("iw,ih,scale", CASES)

@@ -74,5 +74,10 @@ del p
 p = pool(synth.natural_rgba8, 1512, 1680, 8)
 report("C4 stereo 1512x1680->2016x2240 NIS r2.0", dict(useNis=True, renderScale=0.75, sharpness=0.9, radius=2.0), p, 2 * 28224000, "pairs/s")
 report("C4 stereo 1512x1680->2016x2240 NIS r0.5", dict(useNis=True, renderScale=0.75, sharpness=0.9, radius=0.5), p, 2 * 28224000, "pairs/s")
+# NVScaler skips the directional filters of edge-free pixels: the same configuration on content with more edges
+for cname, gen in (("textured (a third of the texels carry an edge)", synth.textured_rgba8), ("uniform noise (84 %: nothing to skip)", synth.uniform_rgba8)):
+    p = pool(gen, 1512, 1680, 8)
+    report("C4 stereo 1512x1680->2016x2240 NIS r2.0, content: " + cname, dict(useNis=True, renderScale=0.75, sharpness=0.9, radius=2.0), p, 2 * 28224000, "pairs/s")
+    del p
 json.dump({"gpu": torch.cuda.get_device_name(0), "note": "1 GPU, device-resident, 2 frames in flight x 1 stream per eye; C4 on 2 GPUs (one eye each) is twice the per-GPU eye rate, C5 is C2 per GPU",
            "results": results}, open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "configs_bench.json"), "w"), indent=1)
