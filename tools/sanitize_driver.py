@@ -78,6 +78,21 @@ for math in (ovr.MATH_STRICT, ovr.MATH_FAST):
         pp.apply(0, torch.from_numpy(np.ascontiguousarray(synth.natural_rgba16f(120, 90, 2).astype(np.float32)[..., :3])).to(dev), fmt=ovr.FORMAT_RGB32F)
         pp.close()
     torch.cuda.synchronize()
+# round 2 (later): both eyes per call on two streams (ovrfsr_apply_pair), NIS on edge-free / mixed / edge-dense content
+for kw in (dict(renderScale=0.75, radius=0.5), dict(renderScale=0.75, radius=0.5, useNis=True), dict(renderScale=1.0, radius=2.0, useNis=True)):
+    pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, sharpness=0.9, **kw))
+    for i in range(3):
+        pp.apply_pair(ovr.to_image(synth.textured_rgba8(331, 203, 20 + i, cell=16), dev), ovr.to_image(synth.natural_rgba8(331, 203, 30 + i), dev))
+    torch.cuda.synchronize()
+    pp.close()
+for gen in (synth.textured_rgba8, synth.uniform_rgba8, lambda w, h, s: np.full((h, w, 4), 90, np.uint8)):
+    for scale in (0.75, 1.0):
+        ow, oh = ovr.output_size(203, 131, scale)
+        ncfg, _ = ovr.make_nis_config(ovr.Config(fsrEnabled=True, useNis=True, renderScale=scale, sharpness=0.7, radius=2.0), scale == 1.0, 0, True, 203, 131, ow, oh)
+        out = ovr.alloc_image(ow, oh, torch.uint8, dev)
+        (ovr.nis_sharpen if scale == 1.0 else ovr.nis_scaler)(ovr.to_image(gen(203, 131, 5), dev), out, ncfg, ovr.MATH_STRICT)
+        n += 1
+torch.cuda.synchronize()
 # front end + stateful path + host entry
 ms = torch.from_numpy(np.repeat(synth.natural_rgba8(90, 61, 7), 4, axis=1)).to(dev)
 pp = ovr.PostProcessor(ovr.Config(fsrEnabled=True, renderScale=0.75, sharpness=0.9, radius=0.5))
