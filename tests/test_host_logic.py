@@ -107,14 +107,40 @@ def test_constants_match_reference_functions():
                           np.ctypeslib.as_array(ref.ref_coef_usm(), (n,)).view(np.uint32))
 
 
+def _round_f32(fr):
+    """Correctly rounded (nearest-even) float32 of an exact Fraction, as a Fraction."""
+    import math
+    from fractions import Fraction as F
+    if fr == 0:
+        return F(0)
+    e = math.floor(math.log2(fr))
+    while F(2) ** e > fr:
+        e -= 1
+    while F(2) ** (e + 1) <= fr:
+        e += 1
+    sc = F(2) ** (23 - e)
+    m = fr * sc
+    fl = m.numerator // m.denominator
+    rem = m - fl
+    if rem > F(1, 2) or (rem == F(1, 2) and fl % 2 == 1):
+        fl += 1
+    return F(fl) / sc
+
+
 def test_unorm8_decode_recipe_is_exact():
-    """device_common.cuh unorm8(): q=v*r, e=fma(-255,q,v), q+=e*r must equal the correctly rounded v/255 for all
-    256 inputs (emulated here with exact double arithmetic and single roundings)."""
-    v = np.arange(256, dtype=np.float64)
-    r = np.float64(np.float32(1.0) / np.float32(255.0))
-    q = (v * r).astype(np.float32).astype(np.float64)
-    e = (v - 255.0 * q).astype(np.float32).astype(np.float64)
-    q2 = (e * r + q).astype(np.float32)
+    """device_common.cuh unorm8(): fma(v, clo, v * chi) with chi = 0x3b808080 (the float below 1/255) and
+    clo = 0x2f808081 (float(1/255 - chi)) must equal the correctly rounded v/255 for all 256 inputs -- checked in exact
+    rational arithmetic with one rounding per device operation."""
+    from fractions import Fraction as F
+    chi = F(float(np.uint32(0x3b808080).view(np.float32)))
+    clo = F(float(np.uint32(0x2f808081).view(np.float32)))
+    assert chi < F(1, 255) and clo == _round_f32(F(1, 255) - chi)
+    got = []
+    for v in range(256):
+        q = _round_f32(v * chi)          # FMUL
+        got.append(_round_f32(v * clo + q))  # FFMA: exact product and sum, one rounding
+        assert got[-1] == _round_f32(F(v, 255)), v
+    q2 = np.array([float(g) for g in got], dtype=np.float32)
     assert np.array_equal(q2, (np.arange(256, dtype=np.float32) / np.float32(255.0)))
     # and encode(decode(v)) == v, which makes RCAS's outside-radius copy an identity on RGBA8
     assert np.array_equal((np.clip(q2, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8), np.arange(256))
