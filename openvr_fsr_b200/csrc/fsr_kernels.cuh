@@ -435,16 +435,17 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
         }
       }
     } else {
-      for (int ty = warp; ty < th; ty += kThreads / 32) {
-        const int gy = clampi(sy0 + ty, 0, a.src.h - 1);
-        const uint8_t *row = a.src.ptr + (size_t)gy * a.src.pitch;
-        for (int tx = lane; tx < cols; tx += 32) {
-          const int gx = clampi(tx0 + tx, 0, a.src.w - 1);
-          float4 c = fetch_texel<FIN>(row, gx);
-          sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y);
-          c.w = 1.0f; // EASU ignores source alpha; the fast path accumulates the tap weight through this lane
-          sC[ty * TW + tx] = c;
-        }
+      // plain loads (FP16 / FP32 sources, unaligned pitch): a flat index over the tile, four texels per thread in
+      // flight (no prefetch hides this latency, unlike the TMA variant)
+      const int nTex = cols * th;
+#pragma unroll 4
+      for (int q = tid; q < nTex; q += kThreads) {
+        const int ty = q / cols, tx = q - ty * cols;
+        const int gy = clampi(sy0 + ty, 0, a.src.h - 1), gx = clampi(tx0 + tx, 0, a.src.w - 1);
+        float4 c = fetch_texel<FIN>(a.src.ptr + (size_t)gy * a.src.pitch, gx);
+        sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y);
+        c.w = 1.0f; // EASU ignores source alpha; the fast path accumulates the tap weight through this lane
+        sC[ty * TW + tx] = c;
       }
     }
     // one row term per output row of the tile for the bilinear fallback (skipped when every group is inside)
