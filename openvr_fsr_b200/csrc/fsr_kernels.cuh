@@ -438,9 +438,10 @@ __global__ void __launch_bounds__(kThreads, 3) easu_kernel(const __grid_constant
       // plain loads (FP16 / FP32 sources, unaligned pitch): a flat index over the tile, four texels per thread in
       // flight (no prefetch hides this latency, unlike the TMA variant)
       const int nTex = cols * th;
+      const uint32_t colsRcp = 0xFFFFFFFFu / (uint32_t)cols + 1u; // ceil(2^32 / cols): q / cols == umulhi(q, colsRcp) for q < 2^32 / cols
 #pragma unroll 4
       for (int q = tid; q < nTex; q += kThreads) {
-        const int ty = q / cols, tx = q - ty * cols;
+        const int ty = (int)__umulhi((uint32_t)q, colsRcp), tx = q - ty * cols;
         const int gy = clampi(sy0 + ty, 0, a.src.h - 1), gx = clampi(tx0 + tx, 0, a.src.w - 1);
         float4 c = fetch_texel<FIN>(a.src.ptr + (size_t)gy * a.src.pitch, gx);
         sL[ty * TW + tx] = c.z * 0.5f + (c.x * 0.5f + c.y);
