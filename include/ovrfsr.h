@@ -117,7 +117,7 @@ typedef struct ovrfsr_config {
 /* Run EASU -> RCAS as ONE fused kernel that keeps the upscaled image in shared memory (same output bits, 79.7 -> 35.0 MB
  * of traffic per C2 eye, one launch) whenever both passes run on the FSR path and the intermediate is UNORM (RGBA8 /
  * RGB10A2).  Off by default: on B200 the pass is instruction-issue-bound, not traffic-bound, and the fused kernel's
- * recomputed ring and lower occupancy make it 10-12 % SLOWER than the two dispatches (DESIGN.md section 5 has the
+ * recomputed ring and lower occupancy make it 10-15 % SLOWER than the two dispatches (DESIGN.md section 5 has the
  * measurements at radius 2.0, 0.5 and 0).  Default (bit clear): the reference's two dispatches (PostProcessor.cpp:586-594),
  * with the outside-radius pixels written straight to the final image by the first one. */
 #define OVRFSR_FLAG_FUSED_FSR 1
